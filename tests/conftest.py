@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long-running CPU check (still part of the default suite)")
+
+
+@pytest.fixture(scope="session")
+def oracle_port():
+    """The C restatement (test infrastructure), built on demand."""
+    from oracle import port
+    port.lib()
+    return port
