@@ -1,0 +1,189 @@
+/* luma_b200.h -- C ABI of the B200-native replacement for LUMA's level-0 time step.
+ *
+ * The reference (cfdemons/LUMA v1.7.12) has no plugin or FFI interface.  The seam this library
+ * plugs into is the member function
+ *
+ *     void GridObj::LBM_multi_opt(int subcycle = 0)        inc/GridObj.h:188
+ *                                                          src/GridObj_ops_lbm_optimised.cpp:36-193
+ *
+ * (sole caller src/main_lbm.cpp:441) together with the halo exchange it ends with,
+ *
+ *     void MpiManager::mpi_communicate(int lev, int reg)   inc/MpiManager.h:238
+ *                                                          src/MpiManager.cpp:631-815
+ *
+ * A LUMA build links a shim translation unit that is still a GridObj member (so it can read the
+ * private fields f, fNew, u, rho, ux_in ... inc/GridObj.h:74-103) and forwards to the entry points
+ * below; INTEGRATION.md shows that shim.  Everything here is extern "C", plain pointers and sizes,
+ * int status returns (0 = ok), no exceptions cross the boundary, no torch types.
+ *
+ * Layouts.  Host arrays are LUMA's own: AoS, flattened as  v + Q*(k + K*(j + M*i))  for f,
+ * d + D*(k + K*(j + M*i)) for u and  k + K*(j + M*i)  for rho / LatTyp (inc/IVector.h:94-134),
+ * x (i) slowest.  The host keeps ownership of everything it passes; the library copies.
+ * Device state (SoA populations, two lattices, packed cell words) is owned by the handle.
+ *
+ * Decomposition.  Level 0 is cut into x-slabs, one per process/GPU (the analogue of
+ * L_MPI_XCORES = nranks, L_MPI_YCORES = L_MPI_ZCORES = 1; slab widths as
+ * MpiManager::mpi_uniformDecompose, src/MpiManager.cpp:1220-1240, see luma_b200_slab()).  The
+ * topology is a periodic ring in x exactly like the reference's MPI_Cart_create(periods = 1,1,1)
+ * (src/MpiManager.cpp:112-136); walls/inlets/outlets in x simply make the wrap unused.
+ * With nranks > 1 the per-step exchange (NCCL point-to-point) replaces mpi_communicate; the
+ * host shim must not call mpi_communicate for level 0.
+ */
+#ifndef LUMA_B200_H
+#define LUMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUMA_B200_ABI_VERSION 1
+
+/* ---- status codes (luma_b200_strerror gives the text; the shim maps non-zero to L_ERROR,
+ *      inc/stdafx.h:135-149) ---- */
+enum {
+	LUMA_B200_OK            = 0,
+	LUMA_B200_EINVAL        = 1,   /* bad argument / inconsistent case */
+	LUMA_B200_ECUDA         = 2,   /* CUDA runtime failure (message kept in the handle) */
+	LUMA_B200_ENCCL         = 3,   /* NCCL failure */
+	LUMA_B200_ENOMEM        = 4,   /* device or host allocation failed */
+	LUMA_B200_EUNSUPPORTED  = 5,   /* a feature outside the level-0 BGK path (KBC, BFL, IBM, refinement ...) */
+	LUMA_B200_ESTATE        = 6,   /* call order: step before upload, comm missing with nranks > 1 ... */
+	LUMA_B200_EBC_NOT_WALL  = 7,   /* a velocity/pressure site has no wall descriptor   (optimised.cpp:334-336) */
+	LUMA_B200_EBC_PRESSURE_EDGE = 8, /* pressure BC on an edge/corner                   (optimised.cpp:357-359) */
+	LUMA_B200_EBC_OFFGRID   = 9    /* extrapolation neighbour off grid                  (optimised.cpp:1387-1390) */
+};
+
+/* eType values the path understands (inc/Enumerations.h:84-96) */
+enum { LUMA_E_SOLID = 0, LUMA_E_FLUID = 1, LUMA_E_REFINED = 2, LUMA_E_VELOCITY = 6, LUMA_E_PRESSURE = 7 };
+
+typedef struct luma_b200 luma_b200_t;
+
+/* Run-time image of the compile-time case (inc/definitions.h) plus the scalars LBM_initGrid
+ * derived from it (src/GridObj_init_grids.cpp:336-344).  Fill with luma_b200_default_params()
+ * first, then overwrite. */
+typedef struct LumaCaseParams {
+	uint32_t struct_size;       /* sizeof(LumaCaseParams), ABI check */
+	int32_t  dims;              /* L_DIMS: 2 or 3 */
+	int32_t  num_vels;          /* L_NUM_VELS: 9 (D2Q9) or 19 (D3Q19), definitions.h:299-309 */
+	int32_t  N, M, K;           /* GLOBAL level-0 size L_N, L_M, L_K (K = 1 in 2-D) */
+	int32_t  rank, nranks;      /* position in the x-ring; 0,1 for the serial build */
+	int32_t  x_offset, x_count; /* first owned global x-plane and number of owned planes
+	                               (luma_b200_slab gives the reference's uniform split) */
+	int32_t  device;            /* CUDA device ordinal for this process */
+	int32_t  regularised;       /* L_REGULARISED_BOUNDARIES (only 1 is supported on the BC path) */
+	int32_t  bgksmag;           /* L_USE_BGKSMAG */
+	double   csmag;             /* L_CSMAG */
+	int32_t  gravity_on;        /* L_GRAVITY_ON */
+	int32_t  gravity_dir;       /* L_GRAVITY_DIRECTION (0,1,2) */
+	double   gravity;           /* GridObj::gravity = fd2flbm(L_GRAVITY_FORCE), inc/GridUnits.h:140 */
+	double   rhoin;             /* L_RHOIN */
+	double   rho_out;           /* L_RHOIN + pd2dlbm(L_PRESSURE_DELTA), optimised.cpp:343-345 */
+	double   dt, dh;            /* GridObj::dt, GridObj::dh */
+	double   omega;             /* GridObj::omega */
+	int32_t  velocity_ramp_on;  /* L_VELOCITY_RAMP defined */
+	double   velocity_ramp;     /* L_VELOCITY_RAMP */
+	int32_t  reynolds_ramp_on;  /* L_REYNOLDS_RAMP defined */
+	double   reynolds_ramp;     /* L_REYNOLDS_RAMP */
+	double   re;                /* L_RE (only read with reynolds_ramp_on) */
+	int32_t  t;                 /* GridObj::t, completed iterations at upload time */
+} LumaCaseParams;
+
+/* Wall descriptor of one velocity/pressure site, exactly what GridUtils::isWithinDomainWall
+ * (src/GridUtils.cpp:1369-1430) returns for it.  `site` indexes the arrays passed to upload. */
+typedef struct LumaSiteBC {
+	int64_t site;
+	int8_t  edge_count;         /* 1 face, 2 edge, 3 corner */
+	int8_t  normal_dir;         /* eCartesianDirection of the last wall hit */
+	int8_t  normal[3];          /* inward normal vector, components in {-1,0,1} */
+	int8_t  pad_[3];
+} LumaSiteBC;
+
+/* Device-side construction of a case too large for (or not worth) the host object model:
+ * the same labelling/initial state LBM_initGrid produces (src/GridObj_init_grids.cpp:155-384,
+ * :983-1097), expressed in cell indices. */
+typedef struct LumaSyntheticCase {
+	int32_t wall_type[6];       /* L_WALL_LEFT, RIGHT, BOTTOM, TOP, FRONT, BACK (eType) */
+	int32_t wall_cells[6];      /* L_WALL_THICKNESS_* in cells (0 = none) */
+	double  u_in[3];            /* uniform inlet/lid velocity in lattice units (ud2ulbm(L_UX0) ...) */
+	const double *ux_in;        /* optional profiles ux_in[j], uy_in[j], uz_in[j] of length M (e.g. the */
+	const double *uy_in;        /* parabola of _LBM_initSetInletProfile, init_grids.cpp:1322-1360);    */
+	const double *uz_in;        /* NULL = the uniform value u_in[d]                                    */
+	int32_t no_flow;            /* L_NO_FLOW */
+	int32_t has_box;            /* bounce-back body as an index box */
+	int32_t box[6];             /* global i0,i1,j0,j1,k0,k1 (half-open) */
+} LumaSyntheticCase;
+
+typedef struct LumaStats {
+	int64_t steps;              /* steps executed through luma_b200_step since create */
+	double  ms_last_call;       /* device time of the last luma_b200_step call (CUDA events) */
+	double  ms_per_step;        /* ms_last_call / nsteps of that call */
+	double  mlups_last_call;    /* owned cells * nsteps / ms_last_call / 1e3 */
+	int64_t kernel_launches;    /* kernels this library launched since create */
+	int64_t halo_bytes_per_step;/* bytes this rank sends per step */
+	int64_t cells;              /* owned cells */
+} LumaStats;
+
+#define LUMA_B200_F   1u
+#define LUMA_B200_RHO 2u
+#define LUMA_B200_U   4u
+
+/* ---- life cycle ---- */
+void luma_b200_default_params(LumaCaseParams *p);
+int  luma_b200_create(luma_b200_t **h, const LumaCaseParams *p);
+void luma_b200_destroy(luma_b200_t *h);
+
+/* The reference's uniform x-decomposition (MpiManager::mpi_uniformDecompose,
+ * src/MpiManager.cpp:1220-1240: ceil(N/G) planes per rank, the last takes the remainder). */
+int  luma_b200_slab(int32_t N, int32_t nranks, int32_t rank, int32_t *x_offset, int32_t *x_count);
+
+/* ---- multi-GPU: attach this process to the ring.  unique_id = the 128 bytes of an ncclUniqueId
+ *      created by rank 0 (luma_b200_comm_unique_id) and broadcast by the host (MPI_Bcast in a
+ *      LUMA MPI build, torch.distributed in bench.py).  Replaces MpiManager::mpi_init /
+ *      mpi_buffer_size for level 0. ---- */
+int  luma_b200_comm_unique_id(void *unique_id_128);
+int  luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128);
+
+/* ---- state in: everything LBM_multi_opt reads (GridObj fields, inc/GridObj.h:74-125).
+ *      Arrays cover this rank's owned planes, preceded/followed by `halo` extra x-planes
+ *      (0 for the serial build, 1 for LUMA's MPI build whose local arrays carry recv layers,
+ *      src/MpiManager.cpp:277-282).  u_aos/rho give the stored macroscopic fields (they matter for
+ *      sites the kernel never updates).  ux_in/uy_in/uz_in have M entries (NULL = zeros). ---- */
+int  luma_b200_upload(luma_b200_t *h, int32_t halo,
+                      const double *f_aos, const double *rho, const double *u_aos,
+                      const int32_t *lattyp,
+                      const LumaSiteBC *bc_sites, size_t n_bc,
+                      const double *ux_in, const double *uy_in, const double *uz_in);
+
+/* ---- state built on the device (benchmark shapes; also usable as a fast LBM_initGrid) ---- */
+int  luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c);
+
+/* ---- nsteps calls of LBM_multi_opt (+ the exchange).  rho/u are kept in registers and stored
+ *      only by the last step of the call, which is when the host may look (main_lbm.cpp:449-561). ---- */
+int  luma_b200_step(luma_b200_t *h, int32_t nsteps);
+
+/* ---- state out, same layout/halo convention as upload; only owned planes are written.
+ *      `what` = LUMA_B200_F | LUMA_B200_RHO | LUMA_B200_U; unused pointers may be NULL. ---- */
+int  luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what,
+                        double *f_aos, double *rho, double *u_aos);
+int  luma_b200_download_lattyp(luma_b200_t *h, int32_t halo, int32_t *lattyp);
+
+/* ---- scalars the host object keeps in step with the device (GridObj::t, ::omega, ::nu) ---- */
+int  luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu);
+
+/* ---- momentum-exchange force on bounce-back bodies accumulated by the LAST step
+ *      (ObjectManager::computeLiftDrag(i,j,k,g), src/ObjectManager.cpp:93-164), this rank's part ---- */
+int  luma_b200_forces(luma_b200_t *h, double F[3]);
+
+int  luma_b200_stats(luma_b200_t *h, LumaStats *s);
+int  luma_b200_sync(luma_b200_t *h);
+const char *luma_b200_strerror(int code);
+const char *luma_b200_last_error(luma_b200_t *h);   /* detail of the last non-zero return */
+int  luma_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMA_B200_H */

@@ -1,0 +1,714 @@
+// api.cu -- the C ABI of include/luma_b200.h: handle, device state, upload/download, the step loop
+// (GridObj::LBM_multi_opt, src/GridObj_ops_lbm_optimised.cpp:36-193) and the slab halo exchange
+// that replaces MpiManager::mpi_communicate (src/MpiManager.cpp:631-815).
+//
+// There is no CPU fallback anywhere in this file: every entry point that touches state needs a
+// CUDA device and fails with LUMA_B200_ECUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "../../include/luma_b200.h"
+#include "kernels.cuh"
+
+using namespace luma;
+
+// ---- NCCL is bound at run time (dlopen), so single-GPU users need no NCCL at all and a host
+//      process that already carries an NCCL (e.g. torch's bundled one) shares it ----
+struct NcclApi
+{
+	void *lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool load(std::string &err)
+	{
+		if (lib) return true;
+		const char *names[] = { "libnccl.so.2", "libnccl.so" };
+		for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+		if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define LUMA_SYM(field, name) *(void **)(&field) = dlsym(lib, name); if (!field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+		LUMA_SYM(GetUniqueId, "ncclGetUniqueId")
+		LUMA_SYM(CommInitRank, "ncclCommInitRank")
+		LUMA_SYM(CommDestroy, "ncclCommDestroy")
+		LUMA_SYM(Send, "ncclSend")
+		LUMA_SYM(Recv, "ncclRecv")
+		LUMA_SYM(GroupStart, "ncclGroupStart")
+		LUMA_SYM(GroupEnd, "ncclGroupEnd")
+		LUMA_SYM(GetErrorString, "ncclGetErrorString")
+#undef LUMA_SYM
+		return true;
+	}
+};
+static NcclApi g_nccl;
+
+struct luma_b200
+{
+	LumaCaseParams p;
+	int Q = 0, D = 0;
+	int ghost = 0;              // 1 when nranks > 1: local planes 0 and P-1 are ghost planes
+	int P = 0;                  // local planes = x_count + 2*ghost
+	long long MK = 0, cells = 0, stride = 0;
+	double *f[2] = { nullptr, nullptr };
+	int cur = 0;
+	uint32_t *cw = nullptr;
+	uint32_t *bcdesc = nullptr;
+	uint8_t *types = nullptr;
+	double *rho = nullptr, *u = nullptr, *uin = nullptr;
+	long long *bc_list = nullptr;
+	int n_bc = 0;
+	void *staging = nullptr;
+	size_t staging_bytes = 0;
+	double *momex_dev = nullptr;
+	cudaStream_t s_main = nullptr, s_comm = nullptr;
+	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	ncclComm_t comm = nullptr;
+	LbmConst C;
+	double omega = 0.0, nu = 0.0;
+	int t = 0;
+	bool have_state = false;
+	bool stepped = false;
+	LumaStats st;
+	std::string err;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return LUMA_B200_ECUDA; } } while (0)
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+	h->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return LUMA_B200_ENCCL; } } while (0)
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+static const double LUMA_PI = 3.14159265358979323846;     // L_PI, inc/stdafx.h:114
+static const double LUMA_SQRT2 = 1.4142135623730950488016887242097;   // L_SQRT2, inc/stdafx.h:113
+
+// GridUtils::getVelocityRampCoefficient, src/GridUtils.cpp:1808-1816
+static double velocity_ramp_coef(const LumaCaseParams &p, double t)
+{
+	if (p.velocity_ramp_on && t <= p.velocity_ramp) return (1.0 - cos(LUMA_PI * t / p.velocity_ramp)) / 2.0;
+	return 1.0;
+}
+// GridUtils::getReynoldsRampCoefficient, src/GridUtils.cpp:1825-1833
+static double reynolds_ramp_coef(const LumaCaseParams &p, double t)
+{
+	if (p.reynolds_ramp_on && t <= p.reynolds_ramp) return 1.0 - cos(LUMA_PI * t / p.reynolds_ramp);
+	return 1.0;
+}
+
+static void make_constants(LbmConst &C, int Q)
+{
+	const volatile double three = 3.0, one = 1.0;     // volatile: evaluate at run time like the reference (src/stdafx.cpp:153)
+	const double cs = one / sqrt(three);
+	C.cs2 = cs * cs;
+	C.inv_cs2 = 1.0 / C.cs2;
+	C.den = (2.0 * C.cs2) * C.cs2;
+	C.inv_den = 1.0 / C.den;
+	C.k1 = 1.0 - C.cs2;
+	C.k0 = 0.0 - C.cs2;
+	if (Q == 19) { C.w[0] = 1.0 / 18.0; C.w[1] = 1.0 / 36.0; C.w[2] = 1.0 / 3.0; }      // src/stdafx.cpp:140-143
+	else { C.w[0] = 1.0 / 9.0; C.w[1] = 1.0 / 36.0; C.w[2] = 4.0 / 9.0; }                // :147-148
+	for (int k = 0; k < 3; ++k) C.wden[k] = C.w[k] / C.den;
+}
+
+extern "C" {
+
+int luma_b200_abi_version(void) { return LUMA_B200_ABI_VERSION; }
+
+const char *luma_b200_strerror(int code)
+{
+	switch (code)
+	{
+	case LUMA_B200_OK: return "ok";
+	case LUMA_B200_EINVAL: return "invalid argument or inconsistent case description";
+	case LUMA_B200_ECUDA: return "CUDA runtime error";
+	case LUMA_B200_ENCCL: return "NCCL error";
+	case LUMA_B200_ENOMEM: return "out of memory";
+	case LUMA_B200_EUNSUPPORTED: return "feature outside the level-0 BGK/Smagorinsky path";
+	case LUMA_B200_ESTATE: return "call out of order";
+	case LUMA_B200_EBC_NOT_WALL: return "Trying to apply a regularised BC on a site not within a wall.";
+	case LUMA_B200_EBC_PRESSURE_EDGE: return "Pressure BC cannot be applied to a corner or an edge.";
+	case LUMA_B200_EBC_OFFGRID: return "Extrapolation site off grid";
+	default: return "unknown luma_b200 status";
+	}
+}
+
+const char *luma_b200_last_error(luma_b200_t *h) { return h ? h->err.c_str() : "null handle"; }
+
+void luma_b200_default_params(LumaCaseParams *p)
+{
+	if (!p) return;
+	memset(p, 0, sizeof(*p));
+	p->struct_size = (uint32_t)sizeof(LumaCaseParams);
+	p->dims = 3; p->num_vels = 19;
+	p->K = 1;
+	p->nranks = 1;
+	p->regularised = 1;
+	p->csmag = 0.3;
+	p->rhoin = 1.0; p->rho_out = 1.0;
+	p->omega = 1.0;
+	p->re = 1.0;
+}
+
+int luma_b200_slab(int32_t N, int32_t nranks, int32_t rank, int32_t *x_offset, int32_t *x_count)
+{
+	if (N < 1 || nranks < 1 || rank < 0 || rank >= nranks) return LUMA_B200_EINVAL;
+	int per = (int)std::ceil((double)N / (double)nranks);
+	int last = per - (per * nranks - N);
+	if (last <= 0)
+	{
+		per = (int)std::floor((double)N / (double)nranks);
+		last = per - (per * nranks - N);
+		if (last <= 0) return LUMA_B200_EINVAL;
+	}
+	if (per < 1) return LUMA_B200_EINVAL;   /* a rank without planes: the reference would build an empty grid */
+	if (x_offset) *x_offset = per * rank;
+	if (x_count) *x_count = (rank == nranks - 1) ? last : per;
+	return LUMA_B200_OK;
+}
+
+static void free_all(luma_b200_t *h)
+{
+	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+	cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->cw); cudaFree(h->bcdesc); cudaFree(h->types);
+	cudaFree(h->rho); cudaFree(h->u); cudaFree(h->uin); cudaFree(h->bc_list); cudaFree(h->staging); cudaFree(h->momex_dev);
+	if (h->ev_edge) cudaEventDestroy(h->ev_edge);
+	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	if (h->s_main) cudaStreamDestroy(h->s_main);
+	if (h->s_comm) cudaStreamDestroy(h->s_comm);
+}
+
+int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
+{
+	if (!out || !p) return LUMA_B200_EINVAL;
+	*out = nullptr;
+	if (p->struct_size != sizeof(LumaCaseParams)) return LUMA_B200_EINVAL;
+	if (!((p->dims == 3 && p->num_vels == 19) || (p->dims == 2 && p->num_vels == 9)))
+		return (p->num_vels == 27) ? LUMA_B200_EUNSUPPORTED : LUMA_B200_EINVAL;
+	if (p->N < 1 || p->M < 2 || p->K < 1 || (p->dims == 2 && p->K != 1)) return LUMA_B200_EINVAL;
+	if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return LUMA_B200_EINVAL;
+	if (p->x_count < 1 || p->x_offset < 0 || p->x_offset + p->x_count > p->N) return LUMA_B200_EINVAL;
+	if (p->nranks == 1 && (p->x_offset != 0 || p->x_count != p->N)) return LUMA_B200_EINVAL;
+	if (p->gravity_on && (p->gravity_dir < 0 || p->gravity_dir >= p->dims)) return LUMA_B200_EINVAL;
+	if (!(p->omega > 0.0)) return LUMA_B200_EINVAL;
+	if (!p->bgksmag && !p->reynolds_ramp_on && p->omega >= 2.0) return LUMA_B200_EINVAL;   // init_grids.cpp:353-356
+
+	luma_b200_t *h = new (std::nothrow) luma_b200();
+	if (!h) return LUMA_B200_ENOMEM;
+	*out = h;       // returned even on failure so that luma_b200_last_error() can be read; destroy it
+	h->p = *p;
+	h->Q = p->num_vels; h->D = p->dims;
+	h->ghost = (p->nranks > 1) ? 1 : 0;
+	h->P = p->x_count + 2 * h->ghost;
+	h->MK = (long long)p->M * p->K;
+	h->cells = (long long)h->P * h->MK;
+	h->stride = (h->cells + 15) / 16 * 16;
+	h->omega = p->omega;
+	h->t = p->t;
+	memset(&h->st, 0, sizeof(h->st));
+	h->st.cells = (long long)p->x_count * h->MK;
+	make_constants(h->C, h->Q);
+	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
+
+	int ndev = 0;
+	CK(cudaGetDeviceCount(&ndev));
+	if (ndev < 1 || p->device < 0 || p->device >= ndev) FAIL(LUMA_B200_ECUDA, "no such CUDA device");
+	CK(cudaSetDevice(p->device));
+	CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+	CK(cudaEventCreate(&h->ev_t0));
+	CK(cudaEventCreate(&h->ev_t1));
+	const size_t fbytes = (size_t)h->stride * h->Q * sizeof(double);
+	cudaError_t e = cudaMalloc(&h->f[0], fbytes);
+	if (e == cudaSuccess) e = cudaMalloc(&h->f[1], fbytes);
+	if (e == cudaSuccess) e = cudaMalloc(&h->cw, (size_t)h->cells * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&h->bcdesc, (size_t)h->cells * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc(&h->types, (size_t)h->cells);
+	if (e == cudaSuccess) e = cudaMalloc(&h->rho, (size_t)h->stride * sizeof(double));
+	if (e == cudaSuccess) e = cudaMalloc(&h->u, (size_t)h->stride * h->D * sizeof(double));
+	if (e == cudaSuccess) e = cudaMalloc(&h->uin, (size_t)3 * p->M * sizeof(double));
+	if (e == cudaSuccess) e = cudaMalloc(&h->momex_dev, (size_t)3 * 4096 * sizeof(double));
+	if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return LUMA_B200_ENOMEM; }
+	CK(cudaMemsetAsync(h->cw, 0, (size_t)h->cells * sizeof(uint32_t), h->s_main));
+	CK(cudaMemsetAsync(h->bcdesc, 0, (size_t)h->cells * sizeof(uint32_t), h->s_main));
+	CK(cudaMemsetAsync(h->uin, 0, (size_t)3 * p->M * sizeof(double), h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	return LUMA_B200_OK;
+}
+
+void luma_b200_destroy(luma_b200_t *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->p.device);
+	cudaDeviceSynchronize();
+	free_all(h);
+	delete h;
+}
+
+int luma_b200_comm_unique_id(void *unique_id_128)
+{
+	std::string err;
+	if (!unique_id_128) return LUMA_B200_EINVAL;
+	if (!g_nccl.load(err)) return LUMA_B200_ENCCL;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) return LUMA_B200_ENCCL;
+	memcpy(unique_id_128, &id, 128);
+	return LUMA_B200_OK;
+}
+
+int luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128)
+{
+	if (!h || !unique_id_128) return LUMA_B200_EINVAL;
+	if (h->p.nranks < 2) FAIL(LUMA_B200_ESTATE, "comm_init on a single-rank handle");
+	if (!g_nccl.load(h->err)) return LUMA_B200_ENCCL;
+	CK(cudaSetDevice(h->p.device));
+	ncclUniqueId id;
+	memcpy(&id, unique_id_128, 128);
+	NK(g_nccl.CommInitRank(&h->comm, h->p.nranks, id, h->p.rank));
+	return LUMA_B200_OK;
+}
+
+static int ensure_staging(luma_b200_t *h, size_t bytes)
+{
+	if (h->staging_bytes >= bytes) return LUMA_B200_OK;
+	if (h->staging) { cudaFree(h->staging); h->staging = nullptr; h->staging_bytes = 0; }
+	if (cudaMalloc(&h->staging, bytes) != cudaSuccess) { cudaGetLastError(); FAIL(LUMA_B200_ENOMEM, "staging buffer"); }
+	h->staging_bytes = bytes;
+	return LUMA_B200_OK;
+}
+
+// populations with c_x = +1 travel to the +x neighbour, c_x = -1 to the -x neighbour
+static int edge_pops(int Q, int sign, int out[8])
+{
+	int n = 0;
+	for (int v = 0; v < Q; ++v)
+	{
+		const int cx = (Q == 19) ? D3Q19::c(v, 0) : D2Q9::c(v, 0);
+		if (cx == sign) out[n++] = v;
+	}
+	return n;
+}
+
+// the exchange step: only the populations that cross the slab face, straight from / into the SoA
+// lattice (each is one contiguous M*K run), ring topology (MPI_Cart_create periodic, MpiManager.cpp:112-136)
+static int exchange_populations(luma_b200_t *h, double *lat, cudaStream_t s)
+{
+	const int n = h->p.nranks, right = (h->p.rank + 1) % n, left = (h->p.rank - 1 + n) % n;
+	int plus[8], minus[8];
+	const int np = edge_pops(h->Q, +1, plus), nm = edge_pops(h->Q, -1, minus);
+	const size_t cnt = (size_t)h->MK;
+	NK(g_nccl.GroupStart());
+	for (int a = 0; a < np; ++a)
+		NK(g_nccl.Send(lat + (long long)plus[a] * h->stride + (long long)(h->P - 2) * h->MK, cnt, ncclFloat64, right, h->comm, s));
+	for (int a = 0; a < np; ++a)
+		NK(g_nccl.Recv(lat + (long long)plus[a] * h->stride, cnt, ncclFloat64, left, h->comm, s));
+	for (int a = 0; a < nm; ++a)
+		NK(g_nccl.Send(lat + (long long)minus[a] * h->stride + h->MK, cnt, ncclFloat64, left, h->comm, s));
+	for (int a = 0; a < nm; ++a)
+		NK(g_nccl.Recv(lat + (long long)minus[a] * h->stride + (long long)(h->P - 1) * h->MK, cnt, ncclFloat64, right, h->comm, s));
+	NK(g_nccl.GroupEnd());
+	return LUMA_B200_OK;
+}
+
+static int exchange_types(luma_b200_t *h, cudaStream_t s)
+{
+	const int n = h->p.nranks, right = (h->p.rank + 1) % n, left = (h->p.rank - 1 + n) % n;
+	const size_t cnt = (size_t)h->MK;
+	NK(g_nccl.GroupStart());
+	NK(g_nccl.Send(h->types + (long long)(h->P - 2) * h->MK, cnt, ncclUint8, right, h->comm, s));
+	NK(g_nccl.Recv(h->types, cnt, ncclUint8, left, h->comm, s));
+	NK(g_nccl.Send(h->types + h->MK, cnt, ncclUint8, left, h->comm, s));
+	NK(g_nccl.Recv(h->types + (long long)(h->P - 1) * h->MK, cnt, ncclUint8, right, h->comm, s));
+	NK(g_nccl.GroupEnd());
+	return LUMA_B200_OK;
+}
+
+// after h->types (owned planes) and h->bcdesc exist on the device: ghost types, validation of the
+// boundary sites the way the reference would L_ERROR on them, boundary list, cell words.
+static int finalize_geometry(luma_b200_t *h)
+{
+	const LumaCaseParams &p = h->p;
+	if (h->ghost)
+	{
+		if (!h->comm) FAIL(LUMA_B200_ESTATE, "nranks > 1 needs luma_b200_comm_init before upload/init");
+		int rc = exchange_types(h, h->s_main);
+		if (rc) return rc;
+	}
+	std::vector<uint8_t> types((size_t)h->cells);
+	std::vector<uint32_t> desc((size_t)h->cells);
+	CK(cudaMemcpyAsync(types.data(), h->types, (size_t)h->cells, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaMemcpyAsync(desc.data(), h->bcdesc, (size_t)h->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+
+	std::vector<long long> list;
+	const int pb = h->ghost, pe = h->P - h->ghost;
+	for (int pl = pb; pl < pe; ++pl)
+		for (int j = 0; j < p.M; ++j)
+			for (int k = 0; k < p.K; ++k)
+			{
+				const long long id = ((long long)pl * p.M + j) * p.K + k;
+				const uint8_t t = types[(size_t)id];
+				if (t == LUMA_E_SOLID || t == LUMA_E_FLUID) continue;
+				if (t != LUMA_E_VELOCITY && t != LUMA_E_PRESSURE)
+					FAIL(LUMA_B200_EUNSUPPORTED, "site type " + std::to_string((int)t) + " (refinement/BFL/slip/extrapolation) is outside the level-0 path");
+				if (!p.regularised)
+					FAIL(LUMA_B200_EUNSUPPORTED, "velocity/pressure sites need L_REGULARISED_BOUNDARIES on this path");
+				const uint32_t d = desc[(size_t)id];
+				const int ec = (int)(d >> CW_EC_SHIFT);
+				if (ec == 0) FAIL(LUMA_B200_EBC_NOT_WALL, luma_b200_strerror(LUMA_B200_EBC_NOT_WALL));
+				if (ec > 1 && t == LUMA_E_PRESSURE) FAIL(LUMA_B200_EBC_PRESSURE_EDGE, luma_b200_strerror(LUMA_B200_EBC_PRESSURE_EDGE));
+				if (ec > 1 || t == LUMA_E_PRESSURE)
+				{
+					int n[3];
+					for (int a = 0; a < 3; ++a) n[a] = (int)((d >> (CW_N_SHIFT + 2 * a)) & 3u) - 1;
+					for (int m = 1; m <= 2; ++m)
+					{
+						const int gi = p.x_offset + (pl - h->ghost) + m * n[0], jj = j + m * n[1], kk = k + m * n[2];
+						if (gi < 0 || gi >= p.N || jj < 0 || jj >= p.M || kk < 0 || kk >= p.K)
+							FAIL(LUMA_B200_EBC_OFFGRID, luma_b200_strerror(LUMA_B200_EBC_OFFGRID));
+						const int pp = pl + m * n[0];
+						if (pp < pb || pp >= pe)
+							FAIL(LUMA_B200_EUNSUPPORTED, "slab too thin: a boundary site extrapolates from a plane owned by another rank");
+						const uint8_t tn = types[(size_t)(((long long)pp * p.M + jj) * p.K + kk)];
+						if (tn != LUMA_E_SOLID && tn != LUMA_E_FLUID)
+							FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from another boundary site (loop-order dependent in the reference)");
+					}
+				}
+				list.push_back(id);
+			}
+	cudaFree(h->bc_list); h->bc_list = nullptr;
+	h->n_bc = (int)list.size();
+	if (h->n_bc)
+	{
+		if (cudaMalloc(&h->bc_list, list.size() * sizeof(long long)) != cudaSuccess) FAIL(LUMA_B200_ENOMEM, "bc list");
+		CK(cudaMemcpyAsync(h->bc_list, list.data(), list.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s_main));
+	}
+	GeomArgs g;
+	g.types = h->types; g.bcdesc = h->bcdesc; g.cw = h->cw;
+	g.P = h->P; g.M = p.M; g.K = p.K; g.wrap_x = h->ghost ? 0 : 1;
+	g.p_begin = pb; g.p_end = pe;
+	if (h->Q == 19) launch_cell_words<D3Q19>(g, h->s_main); else launch_cell_words<D2Q9>(g, h->s_main);
+	h->st.kernel_launches++;
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(h->s_main));
+	return LUMA_B200_OK;
+}
+
+int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const double *rho, const double *u_aos,
+	const int32_t *lattyp, const LumaSiteBC *bc_sites, size_t n_bc,
+	const double *ux_in, const double *uy_in, const double *uz_in)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!f_aos || !rho || !u_aos || !lattyp || halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "upload: null array or bad halo");
+	if (n_bc && !bc_sites) FAIL(LUMA_B200_EINVAL, "upload: bc_sites");
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const long long owned = (long long)p.x_count * h->MK;
+	const long long host_off = (long long)halo * h->MK;       // first owned site in the host arrays
+	const long long dev_off = (long long)h->ghost * h->MK;    // first owned site on the device
+	const long long host_cells = owned + 2 * host_off;
+
+	// populations: AoS chunks -> staging -> SoA lattice 0, then lattice 1 = lattice 0 (f.swap(fNew) keeps
+	// never-updated sites identical in both, optimised.cpp:159 and init_grids.cpp:333)
+	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(192u << 20) / (h->Q * 8)));
+	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
+	if (rc) return rc;
+	for (long long c0 = 0; c0 < owned; c0 += chunk)
+	{
+		const long long n = std::min(chunk, owned - c0);
+		CK(cudaMemcpyAsync(h->staging, f_aos + (host_off + c0) * h->Q, (size_t)n * h->Q * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+		if (h->Q == 19) launch_aos_to_soa<D3Q19>((const double *)h->staging, h->f[0], h->stride, dev_off + c0, n, h->s_main);
+		else launch_aos_to_soa<D2Q9>((const double *)h->staging, h->f[0], h->stride, dev_off + c0, n, h->s_main);
+		h->st.kernel_launches++;
+	}
+	for (long long c0 = 0; c0 < owned; c0 += chunk)
+	{
+		const long long n = std::min(chunk, owned - c0);
+		CK(cudaMemcpyAsync(h->staging, u_aos + (host_off + c0) * h->D, (size_t)n * h->D * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+		launch_u_aos_to_soa((const double *)h->staging, h->u, h->stride, h->D, dev_off + c0, n, h->s_main);
+		h->st.kernel_launches++;
+	}
+	CK(cudaMemcpyAsync(h->rho + dev_off, rho + host_off, (size_t)owned * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+	for (long long c0 = 0; c0 < owned; c0 += chunk * 4)
+	{
+		const long long n = std::min(chunk * 4, owned - c0);
+		CK(cudaMemcpyAsync(h->staging, lattyp + host_off + c0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_main));
+		launch_types_from_i32((const int32_t *)h->staging, h->types + dev_off + c0, n, h->s_main);
+		h->st.kernel_launches++;
+	}
+	CK(cudaMemcpyAsync(h->f[1], h->f[0], (size_t)h->stride * h->Q * sizeof(double), cudaMemcpyDeviceToDevice, h->s_main));
+	h->cur = 0;
+
+	// inlet profiles (inc/GridObj.h:76-78)
+	std::vector<double> uin((size_t)3 * p.M, 0.0);
+	if (ux_in) memcpy(&uin[0], ux_in, sizeof(double) * p.M);
+	if (uy_in) memcpy(&uin[p.M], uy_in, sizeof(double) * p.M);
+	if (uz_in) memcpy(&uin[2 * (size_t)p.M], uz_in, sizeof(double) * p.M);
+	CK(cudaMemcpyAsync(h->uin, uin.data(), uin.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+
+	// wall descriptors of the boundary sites
+	std::vector<uint32_t> desc((size_t)h->cells, 0u);
+	for (size_t b = 0; b < n_bc; ++b)
+	{
+		const LumaSiteBC &s = bc_sites[b];
+		if (s.site < 0 || s.site >= host_cells) FAIL(LUMA_B200_EINVAL, "upload: bc site index out of range");
+		const long long loc = s.site - host_off;
+		if (loc < 0 || loc >= owned) continue;     // descriptor of a halo site: not ours
+		if (s.edge_count < 0 || s.edge_count > 3 || s.normal_dir < 0 || s.normal_dir > 2) FAIL(LUMA_B200_EINVAL, "upload: bc descriptor");
+		desc[(size_t)(loc + dev_off)] = s.edge_count ? cw_pack_bc(s.edge_count, s.normal_dir, s.normal[0], s.normal[1], s.normal[2]) : 0u;
+	}
+	CK(cudaMemcpyAsync(h->bcdesc, desc.data(), desc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_main));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(h->s_main));
+
+	rc = finalize_geometry(h);
+	if (rc) return rc;
+	if (h->ghost)
+	{
+		rc = exchange_populations(h, h->f[h->cur], h->s_main);
+		if (rc) return rc;
+		CK(cudaStreamSynchronize(h->s_main));
+	}
+	h->t = p.t; h->omega = p.omega;
+	h->have_state = true; h->stepped = false;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
+{
+	if (!h || !c) return LUMA_B200_EINVAL;
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	for (int a = 0; a < 6; ++a)
+	{
+		const int t = c->wall_type[a];
+		if (t != LUMA_E_SOLID && t != LUMA_E_FLUID && t != LUMA_E_VELOCITY && t != LUMA_E_PRESSURE)
+			FAIL(LUMA_B200_EUNSUPPORTED, "wall type outside {eSolid,eFluid,eVelocity,ePressure}");
+		if (c->wall_cells[a] < 0) FAIL(LUMA_B200_EINVAL, "negative wall thickness");
+	}
+	std::vector<double> uin((size_t)3 * p.M);
+	const double *prof[3] = { c->ux_in, c->uy_in, c->uz_in };
+	for (int d = 0; d < 3; ++d) for (int j = 0; j < p.M; ++j)
+		uin[(size_t)d * p.M + j] = prof[d] ? prof[d][j] : ((d < h->D) ? c->u_in[d] : 0.0);
+	CK(cudaMemcpyAsync(h->uin, uin.data(), uin.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+
+	SynthArgs a;
+	memset(&a, 0, sizeof(a));
+	a.types = h->types; a.bcdesc = h->bcdesc; a.f0 = h->f[0]; a.f1 = h->f[1]; a.rho = h->rho; a.u = h->u;
+	a.stride = h->stride; a.P = h->P; a.M = p.M; a.K = p.K; a.N = p.N;
+	a.x_first = p.x_offset - h->ghost;
+	for (int i = 0; i < 6; ++i) { a.wall_type[i] = c->wall_type[i]; a.wall_cells[i] = c->wall_cells[i]; a.box[i] = c->box[i]; }
+	a.uin = h->uin;
+	a.ramp0 = velocity_ramp_coef(p, 0.0);
+	a.rhoin = p.rhoin;
+	a.no_flow = c->no_flow; a.has_box = c->has_box;
+	a.C = h->C;
+	if (h->Q == 19) launch_synthetic<D3Q19>(a, h->s_main); else launch_synthetic<D2Q9>(a, h->s_main);
+	h->st.kernel_launches++;
+	CK(cudaGetLastError());
+	h->cur = 0;
+	int rc = finalize_geometry(h);
+	if (rc) return rc;
+	h->t = p.t; h->omega = p.omega;
+	h->have_state = true; h->stepped = false;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_step(luma_b200_t *h, int32_t nsteps)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "step before upload/init_synthetic");
+	if (nsteps < 0) FAIL(LUMA_B200_EINVAL, "nsteps < 0");
+	if (nsteps == 0) return LUMA_B200_OK;
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const bool smag = p.bgksmag != 0, force = p.gravity_on != 0;
+
+	StepArgs a;
+	memset(&a, 0, sizeof(a));
+	a.cw = h->cw; a.rho = h->rho; a.u = h->u; a.stride = h->stride;
+	a.P = h->P; a.M = p.M; a.K = p.K; a.MK = (unsigned)h->MK;
+	a.wrap_x = h->ghost ? 0 : 1;
+	a.C = h->C;
+	a.bc_list = h->bc_list; a.n_bc = h->n_bc; a.uin = h->uin;
+	a.rho_out = p.rho_out;
+	// force_xyz = rho_init * gravity * refinement_ratio along L_GRAVITY_DIRECTION (init_grids.cpp:296-297)
+	for (int d = 0; d < 3; ++d) { a.F[d] = 0.0; a.hF[d] = 0.0; }
+	if (force) { a.F[p.gravity_dir] = p.rhoin * p.gravity * 1.0; a.hF[p.gravity_dir] = 0.5 * a.F[p.gravity_dir]; }
+	a.smag_coef = 2.0 * LUMA_SQRT2 * (p.csmag * p.csmag) * p.rhoin * h->C.cs2 * h->C.cs2;
+
+	CK(cudaEventRecord(h->ev_t0, h->s_main));
+	const int owned = p.x_count;
+	for (int s = 0; s < nsteps; ++s)
+	{
+		if (p.reynolds_ramp_on)
+		{
+			// _LBM_updateReynolds (optimised.cpp:1313-1321), GridUnits::nud2nulbm (inc/GridUnits.h:128)
+			const double newRe = p.re * reynolds_ramp_coef(p, (h->t + 1) * p.dt);
+			h->nu = ((1.0 / newRe) * p.dt) / (p.dh * p.dh);
+			h->omega = 1.0 / ((h->nu / h->C.cs2) + 0.5);
+		}
+		a.omega = h->omega;
+		a.tau = 1.0 / h->omega;
+		for (int k = 0; k < 3; ++k) a.lam[k] = (1 - 0.5 * h->omega) * (h->C.w[k] / h->C.cs2);
+		a.ramp = velocity_ramp_coef(p, (h->t + 1) * p.dt);
+		a.fin = h->f[h->cur]; a.fout = h->f[h->cur ^ 1];
+		a.write_macro = (s == nsteps - 1) ? 1 : 0;
+
+		if (!h->ghost)
+		{
+			if (h->Q == 19) { launch_bc<D3Q19>(a, smag, force, h->s_main, &h->st.kernel_launches); a.p0 = 0; a.pstep = 1; launch_step<D3Q19>(a, smag, force, h->P, h->s_main, &h->st.kernel_launches); }
+			else { launch_bc<D2Q9>(a, smag, force, h->s_main, &h->st.kernel_launches); a.p0 = 0; a.pstep = 1; launch_step<D2Q9>(a, smag, force, h->P, h->s_main, &h->st.kernel_launches); }
+		}
+		else
+		{
+			// slab faces first, then their populations go out on the comm stream while the interior
+			// planes are computed (no overlap exists in the reference: MpiManager.cpp:631 runs after :159)
+			CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
+			StepArgs e = a;
+			e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
+			const int nedge = (owned > 1) ? 2 : 1;
+			StepArgs in = a;
+			in.p0 = 2; in.pstep = 1;
+			if (h->Q == 19) { launch_bc<D3Q19>(a, smag, force, h->s_main, &h->st.kernel_launches); launch_step<D3Q19>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches); }
+			else { launch_bc<D2Q9>(a, smag, force, h->s_main, &h->st.kernel_launches); launch_step<D2Q9>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches); }
+			CK(cudaEventRecord(h->ev_edge, h->s_main));
+			CK(cudaStreamWaitEvent(h->s_comm, h->ev_edge, 0));
+			int rc = exchange_populations(h, h->f[h->cur ^ 1], h->s_comm);
+			if (rc) return rc;
+			CK(cudaEventRecord(h->ev_comm, h->s_comm));
+			if (h->Q == 19) launch_step<D3Q19>(in, smag, force, owned - 2, h->s_main, &h->st.kernel_launches);
+			else launch_step<D2Q9>(in, smag, force, owned - 2, h->s_main, &h->st.kernel_launches);
+		}
+		h->cur ^= 1;
+		++h->t;
+	}
+	if (h->ghost) CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
+	CK(cudaEventRecord(h->ev_t1, h->s_main));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(h->s_main));
+	float ms = 0.f;
+	CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+	h->stepped = true;
+	h->st.steps += nsteps;
+	h->st.ms_last_call = ms;
+	h->st.ms_per_step = ms / nsteps;
+	h->st.mlups_last_call = (double)h->st.cells * nsteps / ((double)ms * 1e3);
+	int plus[8];
+	h->st.halo_bytes_per_step = h->ghost ? 2LL * edge_pops(h->Q, +1, plus) * h->MK * (long long)sizeof(double) : 0;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_aos, double *rho, double *u_aos)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "download before upload/init_synthetic");
+	if (halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "download: halo");
+	if (((what & LUMA_B200_F) && !f_aos) || ((what & LUMA_B200_RHO) && !rho) || ((what & LUMA_B200_U) && !u_aos))
+		FAIL(LUMA_B200_EINVAL, "download: null array");
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const long long owned = (long long)p.x_count * h->MK;
+	const long long host_off = (long long)halo * h->MK, dev_off = (long long)h->ghost * h->MK;
+	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(192u << 20) / (h->Q * 8)));
+	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
+	if (rc) return rc;
+	if (what & LUMA_B200_F)
+		for (long long c0 = 0; c0 < owned; c0 += chunk)
+		{
+			const long long n = std::min(chunk, owned - c0);
+			if (h->Q == 19) launch_soa_to_aos<D3Q19>(h->f[h->cur], (double *)h->staging, h->stride, dev_off + c0, n, h->s_main);
+			else launch_soa_to_aos<D2Q9>(h->f[h->cur], (double *)h->staging, h->stride, dev_off + c0, n, h->s_main);
+			h->st.kernel_launches++;
+			CK(cudaMemcpyAsync(f_aos + (host_off + c0) * h->Q, h->staging, (size_t)n * h->Q * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+		}
+	if (what & LUMA_B200_U)
+		for (long long c0 = 0; c0 < owned; c0 += chunk)
+		{
+			const long long n = std::min(chunk, owned - c0);
+			launch_u_soa_to_aos(h->u, (double *)h->staging, h->stride, h->D, dev_off + c0, n, h->s_main);
+			h->st.kernel_launches++;
+			CK(cudaMemcpyAsync(u_aos + (host_off + c0) * h->D, h->staging, (size_t)n * h->D * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+		}
+	if (what & LUMA_B200_RHO)
+		CK(cudaMemcpyAsync(rho + host_off, h->rho + dev_off, (size_t)owned * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(h->s_main));
+	return LUMA_B200_OK;
+}
+
+int luma_b200_download_lattyp(luma_b200_t *h, int32_t halo, int32_t *lattyp)
+{
+	if (!h || !lattyp) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "download before upload/init_synthetic");
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const long long owned = (long long)p.x_count * h->MK;
+	std::vector<uint8_t> t((size_t)owned);
+	CK(cudaMemcpyAsync(t.data(), h->types + (long long)h->ghost * h->MK, (size_t)owned, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	int32_t *dst = lattyp + (long long)halo * h->MK;
+	for (long long i = 0; i < owned; ++i) dst[i] = (int32_t)t[(size_t)i];
+	return LUMA_B200_OK;
+}
+
+int luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (t) *t = h->t;
+	if (omega) *omega = h->omega;
+	if (nu) *nu = h->nu;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_forces(luma_b200_t *h, double F[3])
+{
+	if (!h || !F) return LUMA_B200_EINVAL;
+	if (!h->have_state || !h->stepped) FAIL(LUMA_B200_ESTATE, "forces need at least one step (they use the pre-stream populations of the last step)");
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const double *prev = h->f[h->cur ^ 1];
+	int nb;
+	if (h->Q == 19) nb = launch_momex<D3Q19>(prev, h->types, h->stride, h->P, p.M, p.K, h->ghost, h->P - h->ghost, p.x_offset - h->ghost, p.N, h->momex_dev, 4096, h->s_main);
+	else nb = launch_momex<D2Q9>(prev, h->types, h->stride, h->P, p.M, p.K, h->ghost, h->P - h->ghost, p.x_offset - h->ghost, p.N, h->momex_dev, 4096, h->s_main);
+	h->st.kernel_launches++;
+	std::vector<double> part((size_t)3 * nb);
+	CK(cudaMemcpyAsync(part.data(), h->momex_dev, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(h->s_main));
+	F[0] = F[1] = F[2] = 0.0;
+	for (int b = 0; b < nb; ++b) { F[0] += part[3 * b]; F[1] += part[3 * b + 1]; F[2] += part[3 * b + 2]; }
+	return LUMA_B200_OK;
+}
+
+int luma_b200_stats(luma_b200_t *h, LumaStats *s)
+{
+	if (!h || !s) return LUMA_B200_EINVAL;
+	*s = h->st;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_sync(luma_b200_t *h)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	CK(cudaSetDevice(h->p.device));
+	CK(cudaStreamSynchronize(h->s_main));
+	CK(cudaStreamSynchronize(h->s_comm));
+	return LUMA_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,566 @@
+// kernels.cu -- sm_100a device code of the level-0 LBM time step (compiled with -fmad=false).
+//
+// One step = k_step over all planes (fluid sites) + k_bc over the list of velocity/pressure sites.
+// Both read lattice `fin` and write lattice `fout` (two-lattice pull scheme, SoA populations), so
+// they are independent of each other and of the order sites are visited in; the reference's
+// loop-order dependent "update the neighbour on the fly" (optimised.cpp:1375-1404) is reproduced by
+// recomputing the neighbour's stream+macro inside the boundary thread from `fin`.
+//
+// Reference for every function: /root/reference/LUMA/src/GridObj_ops_lbm_optimised.cpp (cited as
+// optimised.cpp below).
+#include "kernels.cuh"
+
+namespace luma {
+
+constexpr int STEP_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// pull-stream of one site, GridObj::_LBM_stream_opt (optimised.cpp:206-297): population v comes
+// from site - c_v (periodic by wrap, :216-218) unless that site is eSolid, in which case the
+// site's own opposite population bounces back (:238-243).  All 19 loads are independent.
+// ------------------------------------------------------------------------------------------------
+template <class L>
+__device__ __forceinline__ void pull_populations(const StepArgs &a, const int p, const unsigned r, const long long id,
+	const uint32_t w, double (&f)[L::Q])
+{
+	long long xm = -(long long)a.MK, xp = (long long)a.MK;      // offsets to x-1 / x+1
+	if (a.wrap_x)
+	{
+		if (p == 0) xm = (long long)(a.P - 1) * a.MK;
+		if (p == a.P - 1) xp = -(long long)(a.P - 1) * a.MK;
+	}
+	long long ym = -(long long)a.K, yp = (long long)a.K, zm = -1, zp = 1;
+	if (w & CW_EDGE)
+	{
+		const unsigned j = r / (unsigned)a.K, k = r - j * (unsigned)a.K;
+		if (j == 0) ym = (long long)(a.M - 1) * a.K;
+		if (j == (unsigned)a.M - 1) yp = -(long long)(a.M - 1) * a.K;
+		if (L::D == 3)
+		{
+			if (k == 0) zm = a.K - 1;
+			if (k == (unsigned)a.K - 1) zp = -(long long)(a.K - 1);
+		}
+	}
+	const double *base = a.fin + id;
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		const int cx = L::c(v, 0), cy = L::c(v, 1), cz = L::c(v, 2);
+		long long off = (long long)v * a.stride;
+		if (cx == 1) off += xm; else if (cx == -1) off += xp;
+		if (cy == 1) off += ym; else if (cy == -1) off += yp;
+		if (cz == 1) off += zm; else if (cz == -1) off += zp;
+		if (v < L::Q - 1)
+		{
+			const long long off_bb = (long long)opposite<L>(v) * a.stride;
+			if ((w >> v) & 1u) off = off_bb;
+		}
+		f[v] = __ldg(base + off);
+	}
+}
+
+// BGK(/Smagorinsky) collision with optional Guo forcing, GridObj::_LBM_collide_opt (optimised.cpp:765-790)
+template <class L, bool SMAG, bool FORCE>
+__device__ __forceinline__ void collide(const StepArgs &a, const double (&u)[3], const double (&feq)[L::Q], double (&f)[L::Q])
+{
+	double omega_s = a.omega;
+	if (SMAG) omega_s = smagorinsky_omega<L>(f, feq, a.tau, a.smag_coef);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		if (FORCE)
+			f[v] = f[v] + (omega_s * (feq[v] - f[v]) + guo_force<L>(v, u, a.F, a.C, a.lam));
+		else
+			f[v] = f[v] + omega_s * (feq[v] - f[v]);
+	}
+}
+
+template <class L>
+__device__ __forceinline__ void store_populations(const StepArgs &a, const long long id, const double (&f)[L::Q])
+{
+	double *base = a.fout + id;
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v) base[(long long)v * a.stride] = f[v];
+}
+
+// ------------------------------------------------------------------------------------------------
+// the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
+// ------------------------------------------------------------------------------------------------
+template <class L, bool SMAG, bool FORCE>
+__global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs a)
+{
+	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
+	if (r >= a.MK) return;
+	const int p = a.p0 + (int)blockIdx.y * a.pstep;
+	const long long id = (long long)p * a.MK + r;
+	const uint32_t w = __ldg(a.cw + id);
+	if (cw_class(w) != CLS_FLUID) return;
+
+	double f[L::Q], feq[L::Q], u[3], rho;
+	pull_populations<L>(a, p, r, id, w, f);
+	macroscopic<L, FORCE>(f, a.hF, rho, u);
+	equilibrium_all<L>(rho, u, a.C, feq);
+	collide<L, SMAG, FORCE>(a, u, feq, f);
+	store_populations<L>(a, id, f);
+	if (a.write_macro)
+	{
+		a.rho[id] = rho;
+#pragma unroll
+		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
+	}
+}
+
+// new-time rho,u of an extrapolation neighbour: GridObj::_LBM_updateAndExtrapolate +
+// _LBM_updateInteriorLatticeSite (optimised.cpp:1353-1434).  A fluid neighbour is streamed and
+// "macro'd" from the old lattice here; any other type keeps its stored values (its macro is a no-op).
+template <class L, bool FORCE>
+__device__ __noinline__ void neighbour_macro(const StepArgs &a, const int p, const int j, const int k, double &rho, double (&u)[3])
+{
+	const unsigned r = (unsigned)j * (unsigned)a.K + (unsigned)k;
+	const long long id = (long long)p * a.MK + r;
+	const uint32_t w = a.cw[id];
+	if (cw_class(w) == CLS_FLUID)
+	{
+		double f[L::Q];
+		pull_populations<L>(a, p, r, id, w, f);
+		macroscopic<L, FORCE>(f, a.hF, rho, u);
+	}
+	else
+	{
+		rho = a.rho[id];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) u[d] = (d < L::D) ? a.u[(long long)d * a.stride + id] : 0.0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// velocity / pressure sites: stream, regularised boundary condition, (force), collide.
+// GridObj::_LBM_regularised_opt (optimised.cpp:313-510), one thread per listed site.
+// ------------------------------------------------------------------------------------------------
+template <class L, bool SMAG, bool FORCE>
+__global__ void __launch_bounds__(64) k_bc(const StepArgs a)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.n_bc) return;
+	const long long id = a.bc_list[t];
+	const int p = (int)(id / a.MK);
+	const unsigned r = (unsigned)(id - (long long)p * a.MK);
+	const int j = (int)(r / (unsigned)a.K), k = (int)(r - (unsigned)j * (unsigned)a.K);
+	const uint32_t w = a.cw[id];
+	const bool pressure = cw_class(w) == CLS_PRESSURE;
+	const int ec = (int)(w >> CW_EC_SHIFT);
+	const int nd = (int)((w >> CW_ND_SHIFT) & 3u);
+	int n[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) n[d] = (int)((w >> (CW_N_SHIFT + 2 * d)) & 3u) - 1;
+	const int nn = n[nd == 0 ? 0 : (nd == 1 ? 1 : 2)];
+
+	double f[L::Q];
+	pull_populations<L>(a, p, r, id, w, f);
+
+	// wall velocity (indexed by j whatever the wall, optimised.cpp:338-340) and reference density
+	double uw[3] = { a.uin[j] * a.ramp, a.uin[a.M + j] * a.ramp, a.uin[2 * a.M + j] * a.ramp };
+	double dens = a.rho_out;
+
+	if (ec > 1)
+	{
+		// edge / corner (velocity only): density extrapolated along the normal vector (:364)
+		double r1, r2, u1[3], u2[3];
+		neighbour_macro<L, FORCE>(a, p + n[0], j + n[1], k + n[2], r1, u1);
+		neighbour_macro<L, FORCE>(a, p + 2 * n[0], j + 2 * n[1], k + 2 * n[2], r2, u2);
+		dens = 2.0 * r1 - r2;
+	}
+	else
+	{
+		double f_plus = 0.0, f_zero = 0.0;
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v)
+		{
+			const int cn = (nd == 0) ? L::c(v, 0) : ((nd == 1) ? L::c(v, 1) : L::c(v, 2));
+			if (cn == -nn) f_plus += f[v];
+			else if (cn == 0) f_zero += f[v];
+		}
+		if (pressure)
+		{
+			// tangential velocity: first-order extrapolation of the new-time u (:396-402)
+			double r1, r2, u1[3], u2[3];
+			neighbour_macro<L, FORCE>(a, p + n[0], j + n[1], k + n[2], r1, u1);
+			neighbour_macro<L, FORCE>(a, p + 2 * n[0], j + 2 * n[1], k + 2 * n[2], r2, u2);
+#pragma unroll
+			for (int d = 0; d < L::D; ++d)
+				if (d != nd) uw[d] = 2.0 * u1[d] - u2[d];
+			double un = 1.0 - ((1.0 / dens) * (2.0 * f_plus + f_zero));
+			if (nn == -1) un *= -1.0;
+			if (nd == 0) uw[0] = un; else if (nd == 1) uw[1] = un; else uw[2] = un;
+		}
+		else
+		{
+			double un = (nd == 0) ? uw[0] : ((nd == 1) ? uw[1] : uw[2]);
+			if (nn == -1) un *= -1.0;
+			dens = (1.0 / (1.0 - un)) * (2.0 * f_plus + f_zero);
+		}
+	}
+
+	a.rho[id] = dens;
+#pragma unroll
+	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = uw[d];
+
+	double feq[L::Q];
+	if (L::D == 2) uw[2] = 0.0;
+	equilibrium_all<L>(dens, uw, a.C, feq);
+
+	// non-equilibrium bounce-back on the unknown links, in ascending v with in-place updates (:435-489)
+	double Sxx = 0.0, Syy = 0.0, Sxy = 0.0, Szz = 0.0, Sxz = 0.0, Syz = 0.0;
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		const int c0 = L::c(v, 0), c1 = L::c(v, 1), c2 = L::c(v, 2);
+		const int o = opposite<L>(v);
+		const int cn = (nd == 0) ? c0 : ((nd == 1) ? c1 : c2);
+		if (ec == 1)
+		{
+			if (cn == nn) f[v] = feq[v] + (f[o] - feq[o]);
+		}
+		else if (c0 == n[0] || c1 == n[1] || (L::D == 3 && c2 == n[2]))
+		{
+			const int dp = c0 * n[0] + c1 * n[1] + ((L::D == 3) ? c2 * n[2] : 0);
+			const bool diagonal = (c0 * c0 + c1 * c1 + ((L::D == 3) ? c2 * c2 : 0)) > 1;   // sqrt(|c|^2) > 1.0
+			if (dp == 0 && diagonal) f[v] = feq[v];                                      // buried link (:468-471)
+			else f[v] = feq[v] + (f[o] - feq[o]);
+		}
+		const double fneq = f[v] - feq[v];
+		Sxx += (double)(c0 * c0) * fneq;
+		Syy += (double)(c1 * c1) * fneq;
+		Sxy += (double)(c0 * c1) * fneq;
+		if (L::D == 3)
+		{
+			Szz += (double)(c2 * c2) * fneq;
+			Sxz += (double)(c0 * c2) * fneq;
+			Syz += (double)(c1 * c2) * fneq;
+		}
+	}
+	// regularised populations (:496-508)
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		const int c0 = L::c(v, 0), c1 = L::c(v, 1), c2 = L::c(v, 2);
+		f[v] = feq[v] + a.C.wden[L::wclass(v)] *
+			(
+			(((double)(c0 * c0) - a.C.cs2) * Sxx) +
+			(((double)(c1 * c1) - a.C.cs2) * Syy) +
+			(((double)(c2 * c2) - a.C.cs2) * Szz) +
+			(2.0 * (double)c0 * (double)c1 * Sxy) +
+			(2.0 * (double)c0 * (double)c2 * Sxz) +
+			(2.0 * (double)c1 * (double)c2 * Syz)
+			);
+	}
+
+	// macro is skipped for these types (:803-806); force and collide are applied (:138-150)
+	collide<L, SMAG, FORCE>(a, uw, feq, f);
+	store_populations<L>(a, id, f);
+}
+
+template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches)
+{
+	if (nplanes <= 0) return;
+	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
+	if (smag && force) k_step<L, true, true><<<grid, STEP_THREADS, 0, s>>>(a);
+	else if (smag) k_step<L, true, false><<<grid, STEP_THREADS, 0, s>>>(a);
+	else if (force) k_step<L, false, true><<<grid, STEP_THREADS, 0, s>>>(a);
+	else k_step<L, false, false><<<grid, STEP_THREADS, 0, s>>>(a);
+	if (launches) ++*launches;
+}
+
+template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches)
+{
+	if (a.n_bc <= 0) return;
+	const int threads = 64;
+	dim3 grid((a.n_bc + threads - 1) / threads);
+	if (smag && force) k_bc<L, true, true><<<grid, threads, 0, s>>>(a);
+	else if (smag) k_bc<L, true, false><<<grid, threads, 0, s>>>(a);
+	else if (force) k_bc<L, false, true><<<grid, threads, 0, s>>>(a);
+	else k_bc<L, false, false><<<grid, threads, 0, s>>>(a);
+	if (launches) ++*launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry: cell words from the eType array (+ host- or device-made wall descriptors)
+// ------------------------------------------------------------------------------------------------
+template <class L>
+__global__ void k_cell_words(const GeomArgs g)
+{
+	const unsigned MK = (unsigned)g.M * (unsigned)g.K;
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= MK) return;
+	const int p = g.p_begin + (int)blockIdx.y;
+	const int j = (int)(r / (unsigned)g.K), k = (int)(r - (unsigned)j * (unsigned)g.K);
+	const long long id = (long long)p * MK + r;
+	const uint8_t t = g.types[id];
+	uint32_t cls = CLS_SKIP;
+	if (t == 1) cls = CLS_FLUID; else if (t == 6) cls = CLS_VELOCITY; else if (t == 7) cls = CLS_PRESSURE;
+	uint32_t w = 0;
+	if (cls != CLS_SKIP)
+	{
+		w = cls << CW_CLASS_SHIFT;
+#pragma unroll
+		for (int v = 0; v < L::Q - 1; ++v)
+		{
+			int sp = p - L::c(v, 0), sj = j - L::c(v, 1), sk = k - L::c(v, 2);
+			if (g.wrap_x) sp = (sp + g.P) % g.P;
+			sj = (sj + g.M) % g.M;
+			sk = (sk + g.K) % g.K;
+			const long long src = ((long long)sp * g.M + sj) * g.K + sk;
+			if (g.types[src] == 0) w |= 1u << v;
+		}
+		if (j == 0 || j == g.M - 1 || (L::D == 3 && (k == 0 || k == g.K - 1))) w |= CW_EDGE;
+		if (cls >= CLS_VELOCITY && g.bcdesc) w |= g.bcdesc[id];
+	}
+	g.cw[id] = w;
+}
+
+template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s)
+{
+	const unsigned MK = (unsigned)g.M * (unsigned)g.K;
+	dim3 grid((MK + 255) / 256, (unsigned)(g.p_end - g.p_begin));
+	if (g.p_end > g.p_begin) k_cell_words<L><<<grid, 256, 0, s>>>(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side LBM_initGrid for index-described cases (src/GridObj_init_grids.cpp:155-384):
+// labels (LBM_initBoundLab :983-1097, precedence :1372-1377), u/rho (:37-150), f = feq (:310-333),
+// then the bounce-back body (src/ObjectManager.cpp:309-345), and the wall descriptors
+// (GridUtils::isWithinDomainWall, src/GridUtils.cpp:1369-1430) in cell-index form.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bc_precedence(int current, int desired)
+{
+	if (current == 0 || desired == 0) return 0;
+	if (current == 6) return 6;
+	return desired;
+}
+
+template <class L>
+__global__ void k_synthetic(const SynthArgs a)
+{
+	const unsigned MK = (unsigned)a.M * (unsigned)a.K;
+	const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= MK) return;
+	const int p = (int)blockIdx.y;
+	const int j = (int)(r / (unsigned)a.K), k = (int)(r - (unsigned)j * (unsigned)a.K);
+	const long long id = (long long)p * MK + r;
+	const int gi = ((a.x_first + p) % a.N + a.N) % a.N;
+	const int *wc = a.wall_cells, *wt = a.wall_type;
+
+	int type = 1;
+	if (gi < wc[0]) type = bc_precedence(type, wt[0]);
+	if (gi >= a.N - wc[1]) type = bc_precedence(type, wt[1]);
+	if (L::D == 3)
+	{
+		if (k < wc[4]) type = bc_precedence(type, wt[4]);
+		if (k >= a.K - wc[5]) type = bc_precedence(type, wt[5]);
+	}
+	if (j < wc[2]) type = bc_precedence(type, wt[2]);
+	if (j >= a.M - wc[3]) type = bc_precedence(type, wt[3]);
+
+	double u[3] = { 0.0, 0.0, 0.0 };
+	if (!(a.no_flow && type != 6))
+	{
+#pragma unroll
+		for (int d = 0; d < L::D; ++d) u[d] = a.uin[d * a.M + j] * a.ramp0;
+	}
+	if (type == 0) { u[0] = 0.0; u[1] = 0.0; u[2] = 0.0; }
+	const double rho = a.rhoin;
+
+	double feq[L::Q];
+	equilibrium_all<L>(rho, u, a.C, feq);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		a.f0[(long long)v * a.stride + id] = feq[v];
+		a.f1[(long long)v * a.stride + id] = feq[v];
+	}
+
+	if (a.has_box && type == 1 && gi >= a.box[0] && gi < a.box[1] && j >= a.box[2] && j < a.box[3] && k >= a.box[4] && k < a.box[5])
+	{
+		type = 0;
+		u[0] = 0.0; u[1] = 0.0;   // the reference never zeroes the z component (ObjectManager.cpp:333-338)
+	}
+	a.types[id] = (uint8_t)type;
+	a.rho[id] = rho;
+#pragma unroll
+	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
+
+	int ec = 0, nd = 0, n0 = 0, n1 = 0, n2 = 0;
+	if (gi < wc[0]) { nd = 0; n0 = 1; ++ec; }
+	if (gi >= a.N - wc[1]) { nd = 0; n0 = -1; ++ec; }
+	if (j < wc[2]) { nd = 1; n1 = 1; ++ec; }
+	if (j >= a.M - wc[3]) { nd = 1; n1 = -1; ++ec; }
+	if (L::D == 3)
+	{
+		if (k < wc[4]) { nd = 2; n2 = 1; ++ec; }
+		if (k >= a.K - wc[5]) { nd = 2; n2 = -1; ++ec; }
+	}
+	a.bcdesc[id] = (ec > 0) ? cw_pack_bc(ec, nd, n0, n1, n2) : 0u;
+}
+
+template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s)
+{
+	const unsigned MK = (unsigned)a.M * (unsigned)a.K;
+	dim3 grid((MK + 127) / 128, (unsigned)a.P);
+	k_synthetic<L><<<grid, 128, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion between LUMA's AoS (inc/IVector.h:94-134) and the device SoA
+// ------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, long long stride, long long first, long long n)
+{
+	__shared__ double tile[Q * 64];
+	const long long c0 = (long long)blockIdx.x * 64;
+	const int cnt = (int)((n - c0) < 64 ? (n - c0) : 64);
+	for (int e = threadIdx.x; e < cnt * Q; e += blockDim.x) tile[e] = aos[c0 * Q + e];
+	__syncthreads();
+	for (int e = threadIdx.x; e < cnt * Q; e += blockDim.x)
+	{
+		const int v = e / cnt, c = e - v * cnt;
+		soa[(long long)v * stride + first + c0 + c] = tile[c * Q + v];
+	}
+}
+
+template <int Q>
+__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, long long stride, long long first, long long n)
+{
+	__shared__ double tile[Q * 64];
+	const long long c0 = (long long)blockIdx.x * 64;
+	const int cnt = (int)((n - c0) < 64 ? (n - c0) : 64);
+	for (int e = threadIdx.x; e < cnt * Q; e += blockDim.x)
+	{
+		const int v = e / cnt, c = e - v * cnt;
+		tile[c * Q + v] = soa[(long long)v * stride + first + c0 + c];
+	}
+	__syncthreads();
+	for (int e = threadIdx.x; e < cnt * Q; e += blockDim.x) aos[c0 * Q + e] = tile[e];
+}
+
+template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first, long long n, cudaStream_t s)
+{
+	if (n > 0) k_aos_to_soa<L::Q><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(aos, soa, stride, first, n);
+}
+template <class L> void launch_soa_to_aos(const double *soa, double *aos, long long stride, long long first, long long n, cudaStream_t s)
+{
+	if (n > 0) k_soa_to_aos<L::Q><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(soa, aos, stride, first, n);
+}
+void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int D, long long first, long long n, cudaStream_t s)
+{
+	if (n <= 0) return;
+	if (D == 3) k_aos_to_soa<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(aos, soa, stride, first, n);
+	else k_aos_to_soa<2><<<(unsigned)((n + 63) / 64), 128, 0, s>>>(aos, soa, stride, first, n);
+}
+void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int D, long long first, long long n, cudaStream_t s)
+{
+	if (n <= 0) return;
+	if (D == 3) k_soa_to_aos<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(soa, aos, stride, first, n);
+	else k_soa_to_aos<2><<<(unsigned)((n + 63) / 64), 128, 0, s>>>(soa, aos, stride, first, n);
+}
+
+__global__ void k_types_from_i32(const int32_t *__restrict__ in, uint8_t *__restrict__ out, long long n)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = (uint8_t)in[i];
+}
+__global__ void k_types_to_i32(const uint8_t *__restrict__ in, int32_t *__restrict__ out, long long n)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = (int32_t)in[i];
+}
+void launch_types_from_i32(const int32_t *in, uint8_t *out, long long n, cudaStream_t s)
+{
+	if (n > 0) k_types_from_i32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+}
+void launch_types_to_i32(const uint8_t *in, int32_t *out, long long n, cudaStream_t s)
+{
+	if (n > 0) k_types_to_i32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// momentum exchange on eSolid sites, ObjectManager::computeLiftDrag(i,j,k,g)
+// (src/ObjectManager.cpp:93-164): for every link n of a solid site whose far end (site - c_opp(n))
+// is on the grid and eFluid, add 2 c_opp f_opp(far end), f = populations BEFORE the step.
+// Summation order here: per-thread over n ascending, fixed-shape tree over the block, then the
+// host adds the per-block partials in block order (deterministic; differs from the reference's
+// serial i,j,k order, hence a tolerance in the tests).
+// ------------------------------------------------------------------------------------------------
+template <class L>
+__global__ void __launch_bounds__(256) k_momex(const double *__restrict__ f, const uint8_t *__restrict__ types, long long stride,
+	int P, int M, int K, int p_begin, int p_end, int x_first, int N, double *__restrict__ partials)
+{
+	const long long MK = (long long)M * K;
+	const long long total = (long long)(p_end - p_begin) * MK;
+	double F0 = 0.0, F1 = 0.0, F2 = 0.0;
+	for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x)
+	{
+		const int p = p_begin + (int)(s / MK);
+		const long long r = s - (long long)(p - p_begin) * MK;
+		const int j = (int)(r / K), k = (int)(r - (long long)j * K);
+		const long long id = (long long)p * MK + r;
+		if (types[id] != 0) continue;
+		const int gi = x_first + p;
+#pragma unroll
+		for (int n = 0; n < L::Q; ++n)
+		{
+			const int no = opposite<L>(n);
+			const int xd = gi - L::c(no, 0), yd = j - L::c(no, 1), zd = k - L::c(no, 2);
+			if (xd < 0 || xd >= N || yd < 0 || yd >= M || zd < 0 || zd >= K) continue;
+			const long long dest = ((long long)(p - L::c(no, 0)) * M + yd) * K + zd;
+			if (types[dest] != 1) continue;
+			const double fv = f[(long long)no * stride + dest];
+			F0 += 2.0 * (double)L::c(no, 0) * fv;
+			F1 += 2.0 * (double)L::c(no, 1) * fv;
+			F2 += 2.0 * (double)L::c(no, 2) * fv;
+		}
+	}
+	__shared__ double sh[3][256];
+	sh[0][threadIdx.x] = F0; sh[1][threadIdx.x] = F1; sh[2][threadIdx.x] = F2;
+	__syncthreads();
+	for (int w = 128; w > 0; w >>= 1)
+	{
+		if ((int)threadIdx.x < w)
+		{
+			sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
+			sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
+			sh[2][threadIdx.x] += sh[2][threadIdx.x + w];
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		partials[3 * blockIdx.x + 0] = sh[0][0];
+		partials[3 * blockIdx.x + 1] = sh[1][0];
+		partials[3 * blockIdx.x + 2] = sh[2][0];
+	}
+}
+
+template <class L> int launch_momex(const double *f_prev, const uint8_t *types, long long stride, int P, int M, int K,
+	int p_begin, int p_end, int x_first, int N, double *partials, int max_blocks, cudaStream_t s)
+{
+	const long long total = (long long)(p_end - p_begin) * M * K;
+	int blocks = (int)((total + 255) / 256);
+	if (blocks > max_blocks) blocks = max_blocks;
+	if (blocks < 1) blocks = 1;
+	k_momex<L><<<blocks, 256, 0, s>>>(f_prev, types, stride, P, M, K, p_begin, p_end, x_first, N, partials);
+	return blocks;
+}
+
+// explicit instantiations
+#define LUMA_INST(L) \
+	template void launch_step<L>(const StepArgs &, bool, bool, int, cudaStream_t, int64_t *); \
+	template void launch_bc<L>(const StepArgs &, bool, bool, cudaStream_t, int64_t *); \
+	template void launch_cell_words<L>(const GeomArgs &, cudaStream_t); \
+	template void launch_synthetic<L>(const SynthArgs &, cudaStream_t); \
+	template void launch_aos_to_soa<L>(const double *, double *, long long, long long, long long, cudaStream_t); \
+	template void launch_soa_to_aos<L>(const double *, double *, long long, long long, long long, cudaStream_t); \
+	template int launch_momex<L>(const double *, const uint8_t *, long long, int, int, int, int, int, int, int, double *, int, cudaStream_t);
+LUMA_INST(D3Q19)
+LUMA_INST(D2Q9)
+
+}  // namespace luma

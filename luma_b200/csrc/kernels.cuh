@@ -1,0 +1,83 @@
+// kernels.cuh -- argument blocks and launchers shared by kernels.cu (device code) and api.cu (host).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "lattice.cuh"
+
+namespace luma {
+
+struct StepArgs
+{
+	const double *fin;        // lattice read by this step   [Q][stride]
+	double *fout;             // lattice written by this step
+	const uint32_t *cw;       // cell words [cells]
+	double *rho;              // [cells]
+	double *u;                // SoA [D][stride]
+	long long stride;         // elements between populations (>= cells, multiple of 16)
+	int P, M, K;              // local planes (incl. ghost planes when !wrap_x), rows, columns
+	unsigned MK;              // M*K
+	int wrap_x;               // 1: periodic wrap inside the array (single rank); 0: ghost planes 0 and P-1
+	int p0, pstep;            // plane handled by blockIdx.y: p0 + blockIdx.y * pstep
+	int write_macro;          // store rho,u of fluid sites (last step of a call)
+	double omega;
+	double tau;               // 1.0 / omega
+	double smag_coef;         // 2.0*L_SQRT2*SQ(L_CSMAG)*L_RHOIN*SQ(cs)*SQ(cs)          optimised.cpp:752
+	double lam[3];            // (1 - 0.5*omega) * (w/(cs*cs)) per weight class            optimised.cpp:962
+	double F[3];              // force_xyz (uniform: rho_init * gravity along one axis)    init_grids.cpp:296
+	double hF[3];             // 0.5 * F
+	LbmConst C;
+	// boundary sites
+	const long long *bc_list; // local site ids of velocity/pressure sites
+	int n_bc;
+	const double *uin;        // [3][M] ux_in, uy_in, uz_in
+	double ramp;              // getVelocityRampCoefficient((t+1)*dt)
+	double rho_out;
+};
+
+struct GeomArgs
+{
+	const uint8_t *types;     // eType per cell [cells]
+	const uint32_t *bcdesc;   // cw_pack_bc() bits per cell or nullptr
+	uint32_t *cw;
+	int P, M, K;
+	int wrap_x;
+	int p_begin, p_end;       // planes that get a cell word (owned planes)
+};
+
+struct SynthArgs
+{
+	uint8_t *types;
+	uint32_t *bcdesc;
+	double *f0, *f1;
+	double *rho, *u;
+	long long stride;
+	int P, M, K;
+	int N;                    // global x size
+	int x_first;              // global x index of local plane 0 (may be -1 / wrap)
+	int wall_type[6];
+	int wall_cells[6];
+	double uin_uniform[3];
+	const double *uin;        // [3][M] profiles (filled on host)
+	double ramp0;
+	double rhoin;
+	int no_flow;
+	int has_box;
+	int box[6];
+	LbmConst C;
+};
+
+template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches);
+template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches);
+template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
+template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);
+template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first_cell, long long ncells, cudaStream_t s);
+template <class L> void launch_soa_to_aos(const double *soa, double *aos, long long stride, long long first_cell, long long ncells, cudaStream_t s);
+void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int D, long long first_cell, long long ncells, cudaStream_t s);
+void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int D, long long first_cell, long long ncells, cudaStream_t s);
+void launch_types_from_i32(const int32_t *in, uint8_t *out, long long n, cudaStream_t s);
+void launch_types_to_i32(const uint8_t *in, int32_t *out, long long n, cudaStream_t s);
+// momentum exchange: per-block partial sums [nblocks][3]; returns nblocks
+template <class L> int launch_momex(const double *f_prev, const uint8_t *types, long long stride, int P, int M, int K,
+	int p_begin, int p_end, int x_first, int N, double *partials, int max_blocks, cudaStream_t s);
+
+}  // namespace luma

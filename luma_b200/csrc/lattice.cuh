@@ -1,0 +1,236 @@
+// lattice.cuh -- lattice tables and the exact (reference-order) fp64 arithmetic of the LBM step.
+//
+// Everything here restates arithmetic of /root/reference/LUMA/src/GridObj_ops_lbm_optimised.cpp so
+// that the CUDA path is bit-identical with the reference's CPU build (g++ -O3, x86-64 baseline:
+// IEEE double, no FMA contraction, no reassociation).  Rules kept throughout:
+//   * every sum is evaluated left to right in the reference's term order; terms the reference
+//     multiplies by an integer 0 are dropped (adding +-0 never changes a running IEEE sum that is
+//     later added to a non-zero value); multiplications by +-1 / +-2 are exact sign/exponent changes;
+//   * this translation unit is compiled with -fmad=false: no contraction anywhere, the only fused
+//     operations are the explicit fma() calls in div_const();
+//   * x / cs^2 and x / (2 cs^4) are divisions by run-time CONSTANTS; div_const() evaluates them with
+//     one multiply and two FMAs and is correctly rounded for these two divisors for every normal x
+//     (proof by enumeration of the candidate failures: tests/test_constdiv_exact.py), i.e. it
+//     returns exactly what the reference's `/` returns.
+#pragma once
+#include <cstdint>
+
+namespace luma {
+
+// ---- direction tables: src/stdafx.cpp:81-102 (D3Q19), :114-125 (D2Q9); rest population last;
+//      opposites are (v ^ 1) for v < Q-1 (src/GridUtils.cpp:54-55, :66-67) ----
+struct D3Q19
+{
+	static constexpr int Q = 19;
+	static constexpr int D = 3;
+	__host__ __device__ static constexpr int c(int v, int d)
+	{
+		constexpr int T[19][3] = {
+			{ 1, 0, 0 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, -1, 0 }, { 0, 0, 1 }, { 0, 0, -1 },
+			{ 1, 1, 0 }, { -1, -1, 0 }, { 1, -1, 0 }, { -1, 1, 0 },
+			{ 0, 1, 1 }, { 0, -1, -1 }, { 0, 1, -1 }, { 0, -1, 1 },
+			{ 1, 0, 1 }, { -1, 0, -1 }, { -1, 0, 1 }, { 1, 0, -1 }, { 0, 0, 0 } };
+		return T[v][d];
+	}
+	// weight class: 0 -> 1/18, 1 -> 1/36, 2 -> 1/3   (src/stdafx.cpp:140-143)
+	__host__ __device__ static constexpr int wclass(int v) { return v < 6 ? 0 : (v < 18 ? 1 : 2); }
+};
+
+struct D2Q9
+{
+	static constexpr int Q = 9;
+	static constexpr int D = 2;
+	__host__ __device__ static constexpr int c(int v, int d)
+	{
+		constexpr int T[9][3] = {
+			{ 1, 0, 0 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, -1, 0 },
+			{ 1, 1, 0 }, { -1, -1, 0 }, { 1, -1, 0 }, { -1, 1, 0 }, { 0, 0, 0 } };
+		return T[v][d];
+	}
+	// weight class: 0 -> 1/9, 1 -> 1/36, 2 -> 4/9   (src/stdafx.cpp:147-148)
+	__host__ __device__ static constexpr int wclass(int v) { return v < 4 ? 0 : (v < 8 ? 1 : 2); }
+};
+
+template <class L> __host__ __device__ constexpr int opposite(int v) { return v == L::Q - 1 ? v : (v ^ 1); }
+
+// ---- constants derived on the host exactly as the reference derives them ----
+struct LbmConst
+{
+	double cs2;       // SQ(cs), cs = 1.0/sqrt(3.0)                         src/stdafx.cpp:153
+	double inv_cs2;   // 1.0 / cs2   (correctly rounded, host division)
+	double den;       // (2.0 * cs2) * cs2                                   optimised.cpp:704
+	double inv_den;   // 1.0 / den
+	double k1;        // 1.0 - cs2   = (SQ(c) - SQ(cs)) for c = +-1
+	double k0;        // 0.0 - cs2   for c = 0
+	double w[3];      // lattice weights by class
+	double wden[3];   // w[cls] / den                                        optimised.cpp:498
+};
+
+// correctly rounded a / b for the two constant divisors (y = RN(1/b)); see header comment
+__device__ __forceinline__ double div_const(double a, double b, double y)
+{
+	const double q = a * y;
+	const double r = fma(-q, b, a);
+	return fma(r, y, q);
+}
+
+// ---- cell word (one uint32 per site, built once by build_cell_words) ----
+//  bits  0..18  link v bounces back: the site this population is pulled from is eSolid  (optimised.cpp:238)
+//  bits 19..20  class: 0 not updated (eSolid/eRefined), 1 eFluid, 2 eVelocity, 3 ePressure
+//  bit   21     site lies on the first/last row or column of the array (periodic wrap needed in y or z)
+//  bits 22..23  normalDirection          } regularised-BC descriptor of velocity/pressure sites,
+//  bits 24..29  normal vector + 1 (2b x3)} GridUtils::isWithinDomainWall, src/GridUtils.cpp:1369
+//  bits 30..31  edgeCount                }
+enum : uint32_t { CW_LINKS = 0x7FFFFu, CW_CLASS_SHIFT = 19, CW_EDGE = 1u << 21, CW_ND_SHIFT = 22, CW_N_SHIFT = 24, CW_EC_SHIFT = 30 };
+enum : uint32_t { CLS_SKIP = 0, CLS_FLUID = 1, CLS_VELOCITY = 2, CLS_PRESSURE = 3 };
+
+__host__ __device__ inline uint32_t cw_class(uint32_t w) { return (w >> CW_CLASS_SHIFT) & 3u; }
+__host__ __device__ inline uint32_t cw_pack_bc(int ec, int nd, int nx, int ny, int nz)
+{
+	return ((uint32_t)(ec & 3) << CW_EC_SHIFT) | ((uint32_t)(nd & 3) << CW_ND_SHIFT) |
+		((uint32_t)((nx + 1) | ((ny + 1) << 2) | ((nz + 1) << 4)) << CW_N_SHIFT);
+}
+
+// ---- equilibrium for all Q directions, GridObj::_LBM_equilibrium_opt (optimised.cpp:674-705):
+//        feq = rho * w[v] * (1.0 + (A / SQ(cs)) + (B / (2.0 * SQ(cs) * SQ(cs))))
+//      evaluated per opposite pair: A(opp) = -A and B(opp) = B hold exactly in IEEE arithmetic. ----
+template <class L>
+__device__ __forceinline__ void equilibrium_all(const double rho, const double (&u)[3], const LbmConst &C, double (&feq)[L::Q])
+{
+	double t1[3], t0[3];
+#pragma unroll
+	for (int d = 0; d < L::D; ++d)
+	{
+		const double s = u[d] * u[d];
+		t1[d] = C.k1 * s;
+		t0[d] = C.k0 * s;
+	}
+	// 2*ca*cb*ua*ub evaluates as ((+-2) * ua) * ub
+	const double x01 = (2.0 * u[0]) * u[1];
+	const double x02 = (L::D == 3) ? (2.0 * u[0]) * u[2] : 0.0;
+	const double x12 = (L::D == 3) ? (2.0 * u[1]) * u[2] : 0.0;
+	double rw[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) rw[k] = rho * C.w[k];
+
+#pragma unroll
+	for (int v = 0; v < L::Q - 1; v += 2)
+	{
+		const int c0 = L::c(v, 0), c1 = L::c(v, 1), c2 = L::c(v, 2);
+		double A = 0.0;
+		bool first = true;
+		if (c0 != 0) { A = (c0 > 0) ? u[0] : -u[0]; first = false; }
+		if (c1 != 0) { const double t = (c1 > 0) ? u[1] : -u[1]; A = first ? t : A + t; first = false; }
+		if (L::D == 3 && c2 != 0) { const double t = (c2 > 0) ? u[2] : -u[2]; A = first ? t : A + t; first = false; }
+		double B = (c0 ? t1[0] : t0[0]) + (c1 ? t1[1] : t0[1]);
+		if (L::D == 3) B = B + (c2 ? t1[2] : t0[2]);
+		if (c0 * c1 != 0) B = B + ((c0 * c1 > 0) ? x01 : -x01);
+		if (L::D == 3 && c0 * c2 != 0) B = B + ((c0 * c2 > 0) ? x02 : -x02);
+		if (L::D == 3 && c1 * c2 != 0) B = B + ((c1 * c2 > 0) ? x12 : -x12);
+		const double qa = div_const(A, C.cs2, C.inv_cs2);
+		const double qb = div_const(B, C.den, C.inv_den);
+		const double r = rw[L::wclass(v)];
+		feq[v] = r * ((1.0 + qa) + qb);
+		feq[v + 1] = r * ((1.0 - qa) + qb);
+	}
+	{
+		double B = t0[0] + t0[1];
+		if (L::D == 3) B = B + t0[2];
+		const double qb = div_const(B, C.den, C.inv_den);
+		feq[L::Q - 1] = rw[2] * (1.0 + qb);
+	}
+}
+
+// ---- rho = sum f, rho*u = sum c f (+ F/2), GridObj::_LBM_macro_opt (optimised.cpp:800-847) ----
+template <class L, bool FORCE>
+__device__ __forceinline__ void macroscopic(const double (&f)[L::Q], const double (&hF)[3], double &rho, double (&u)[3])
+{
+	double r = f[0];
+	double m[3] = { 0.0, 0.0, 0.0 };
+	bool first[3] = { true, true, true };
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		if (v > 0) r = r + f[v];
+#pragma unroll
+		for (int d = 0; d < L::D; ++d)
+		{
+			const int c = L::c(v, d);
+			if (c != 0)
+			{
+				const double t = (c > 0) ? f[v] : -f[v];
+				m[d] = first[d] ? t : m[d] + t;
+				first[d] = false;
+			}
+		}
+	}
+	if (FORCE)
+	{
+		m[0] = m[0] + hF[0];
+		m[1] = m[1] + hF[1];
+		if (L::D == 3) m[0] = m[0] + hF[2];   // sic: the reference adds F_z/2 to the x momentum (optimised.cpp:833)
+	}
+	rho = r;
+	u[0] = m[0] / r;
+	u[1] = m[1] / r;
+	u[2] = (L::D == 3) ? m[2] / r : 0.0;
+}
+
+// ---- Smagorinsky relaxation, GridObj::_LBM_smag (optimised.cpp:717-756) with Matrix2D::operator%
+//      (inc/Matrix.h:65-75): returns omega_s ----
+template <class L>
+__device__ __forceinline__ double smagorinsky_omega(const double (&f)[L::Q], const double (&feq)[L::Q], const double tau, const double smag_coef)
+{
+	double S[3][3] = { { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
+	bool first[3][3] = { { true, true, true }, { true, true, true }, { true, true, true } };
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		const double fneq = f[v] - feq[v];
+#pragma unroll
+		for (int a = 0; a < L::D; ++a)
+#pragma unroll
+			for (int b = a; b < L::D; ++b)
+			{
+				const int cc = L::c(v, a) * L::c(v, b);
+				if (cc != 0)
+				{
+					const double t = (cc > 0) ? fneq : -fneq;
+					S[a][b] = first[a][b] ? t : S[a][b] + t;
+					first[a][b] = false;
+				}
+			}
+	}
+#pragma unroll
+	for (int a = 1; a < L::D; ++a)
+#pragma unroll
+		for (int b = 0; b < a; ++b) S[a][b] = S[b][a];
+	double total = 0.0;
+#pragma unroll
+	for (int a = 0; a < L::D; ++a)
+	{
+		double row = S[a][0] * S[a][0];
+#pragma unroll
+		for (int b = 1; b < L::D; ++b) row = row + S[a][b] * S[a][b];
+		total = (a == 0) ? row : total + row;
+	}
+	const double Qm = sqrt(2.0 * total);
+	const double tau_t = 0.5 * (sqrt((tau * tau) + smag_coef * Qm) - tau);
+	return 1.0 / (tau + tau_t);
+}
+
+// ---- Guo forcing term of one direction, GridObj::_LBM_forceGrid_opt (optimised.cpp:959-989) ----
+template <class L>
+__device__ __forceinline__ double guo_force(const int v, const double (&u)[3], const double (&F)[3], const LbmConst &C, const double (&lam)[3])
+{
+	double beta = 0.0;
+#pragma unroll
+	for (int d = 0; d < L::D; ++d) beta = beta + ((double)L::c(v, d) * u[d]);
+	beta = beta * C.inv_cs2;
+	double fi = 0.0;
+#pragma unroll
+	for (int d = 0; d < L::D; ++d) fi = fi + F[d] * ((double)L::c(v, d) * (1.0 + beta) - u[d]);
+	return fi * lam[L::wclass(v)];
+}
+
+}  // namespace luma

@@ -1,0 +1,164 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (luma_b200.GridObj ->
+include/luma_b200.h), against the oracle on identical inputs.
+
+Bar (BASELINE.json north_star): max relative error <= 1e-12 on f, rho, u after 1000 steps.
+What is asserted here is stronger: BIT-FOR-BIT equality with the oracle (which is itself pinned
+bit-for-bit to the compiled reference), and equality with the committed reference digests in
+tests/golden/.  Reductions: none on the path (per-site sums are fixed-order).
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import luma_b200
+from luma_b200 import capi
+from oracle import port
+from oracle.cases import CASES
+from util import defs_from_case, first_diff, max_rel_err
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-12     # north_star tolerance; the assertions below demand exact equality
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _golden(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as fh:
+        return json.load(fh)
+
+
+def _assert_same(name, tag, got, ref):
+    for nm in ("f", "rho", "u"):
+        a, b = got[nm], getattr(ref, nm)
+        assert max_rel_err(a, b) <= TOL, (name, tag, nm, first_diff(a, b))
+        assert np.array_equal(a, b), "%s %s %s: %s" % (name, tag, nm, first_diff(a, b))
+
+
+def _steps(case, cap):
+    return [s for s in case.steps if s <= cap]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_upload_path_bitwise_vs_oracle(name):
+    """Drop-in flow: the host (here the oracle standing in for LUMA's LBM_initGrid) owns the state,
+    uploads it, steps on the GPU, downloads at the reference's snapshot steps."""
+    case = CASES[name]
+    ref = port.PortGrid(case)
+    g = luma_b200.GridObj(defs_from_case(case))
+    g.upload(ref.f, ref.rho, ref.u, ref.lattyp, ref.uin(0), ref.uin(1), ref.uin(2))
+    _assert_same(name, "init", g.download(), ref)
+    gold = _golden(name)
+    cap = 1000 if case.N * case.M * case.K <= 70000 else 100
+    for s in _steps(case, cap):
+        g.LBM_multi_opt(s - g.t)
+        ref.step(s - ref.t)
+        assert g.t == ref.t == s
+        assert g.omega == ref.omega
+        got = g.download()
+        _assert_same(name, "t%d" % s, got, ref)
+        snap = gold["snapshots"]["t%d" % s]
+        assert (snap["f"], snap["rho"], snap["u"]) == (_digest(got["f"]), _digest(got["rho"]), _digest(got["u"]))
+    g.close(); ref.close()
+
+
+@pytest.mark.parametrize("name", [n for n in CASES])
+def test_device_init_path_bitwise_vs_oracle(name):
+    """State built on the device (luma_b200_init_synthetic, the LBM_initGrid equivalent) must equal the
+    reference's initial state and evolve identically."""
+    case = CASES[name]
+    ref = port.PortGrid(case)
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    assert np.array_equal(g.LatTyp, ref.lattyp), first_diff(g.LatTyp, ref.lattyp)
+    _assert_same(name, "init", g.download(), ref)
+    for s in _steps(case, 100):
+        g.LBM_multi_opt(s - g.t)
+        ref.step(s - ref.t)
+        _assert_same(name, "t%d" % s, g.download(), ref)
+    g.close(); ref.close()
+
+
+def test_single_step_calls_equal_batched_calls():
+    case = CASES["cyl2d"]
+    a = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    b = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    a.LBM_multi_opt(37)
+    for _ in range(37):
+        b.LBM_multi_opt()
+    da, db = a.download(), b.download()
+    for nm in ("f", "rho", "u"):
+        assert np.array_equal(da[nm], db[nm]), nm
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["cyl3d", "cyl2d"])
+def test_momentum_exchange_force(name):
+    """ObjectManager::computeLiftDrag: cross-site sum, order differs from the reference's serial i,j,k
+    order (tree per block, then blocks ascending) -> tolerance 1e-10 relative to sum |terms|."""
+    case = CASES[name]
+    ref = port.PortGrid(case)
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    for s in (1, 10, 100):
+        g.LBM_multi_opt(s - g.t)
+        ref.step(s - ref.t)
+        F, Fr = g.computeLiftDrag(), ref.force
+        scale = max(1.0, float(np.abs(Fr).max()))
+        assert np.all(np.abs(F - Fr) <= 1e-10 * scale), (name, s, F, Fr)
+    g.close(); ref.close()
+
+
+def test_unsupported_and_fatal_conditions_are_reported():
+    case = CASES["tunnel2d"]
+    ref = port.PortGrid(case)
+    d = defs_from_case(case)
+    g = luma_b200.GridObj(d)
+    # a velocity site without a wall descriptor -> the reference's "not within a wall" L_ERROR
+    with pytest.raises(capi.LumaB200Error) as e:
+        g.upload(ref.f, ref.rho, ref.u, ref.lattyp, bc_sites=[])
+    assert e.value.code == capi.EBC_NOT_WALL
+    # step before any state
+    g2 = luma_b200.GridObj(d)
+    with pytest.raises(capi.LumaB200Error) as e:
+        g2.LBM_multi_opt()
+    assert e.value.code == capi.ESTATE
+    # refinement labels are outside the level-0 path
+    lt = ref.lattyp.copy(); lt[lt.size // 2] = 2
+    with pytest.raises(capi.LumaB200Error) as e:
+        g2.upload(ref.f, ref.rho, ref.u, lt)
+    assert e.value.code == capi.EUNSUPPORTED
+    g.close(); g2.close(); ref.close()
+
+
+def test_full_size_c2_properties():
+    """BASELINE configs[1] at full size (256^3, 16.8 M cells) cannot be replayed by the oracle in
+    seconds; check size-independent properties instead: mass conservation in the closed cavity
+    away from the lid rows is not exact (lid BC), so use (a) determinism: two runs are bit-identical,
+    (b) the solid frame never changes, (c) z-mirror symmetry of the cavity flow is preserved exactly
+    for the symmetric populations."""
+    d = luma_b200.Definitions(L_DIMS=3, L_RESOLUTION=256, L_TIMESTEP=0.05 / 256.0, L_RE=1000.0,
+                              L_WALL_TOP=luma_b200.eVelocity)
+    a = luma_b200.GridObj(d).LBM_initGrid()
+    f0 = a.download(capi.F)["f"].reshape(256, 256, 256, 19)
+    a.LBM_multi_opt(20)
+    ra = a.download(capi.RHO | capi.U)
+    fa = a.download(capi.F)["f"].reshape(256, 256, 256, 19)
+    lt = a.LatTyp.reshape(256, 256, 256)
+    assert np.array_equal(fa[lt == 0], f0[lt == 0])
+    rho = ra["rho"].reshape(256, 256, 256)
+    u = ra["u"].reshape(256, 256, 256, 3)
+    assert np.isfinite(rho).all() and abs(rho[lt == 1].mean() - 1.0) < 1e-6
+    # mirror symmetry in z: rho(k) == rho(K-1-k), ux, uy even, uz odd -- exact because the arithmetic
+    # of mirrored populations is the same sequence of operations on mirrored operands only when the
+    # direction order is mirror-symmetric; D3Q19's numbering is not, so allow round-off here
+    assert np.max(np.abs(rho - rho[:, :, ::-1])) < 1e-13
+    assert np.max(np.abs(u[..., 2] + u[:, :, ::-1, 2])) < 1e-13
+    a.close()
+    b = luma_b200.GridObj(d).LBM_initGrid()
+    b.LBM_multi_opt(20)
+    assert np.array_equal(b.download(capi.RHO)["rho"], ra["rho"])
+    b.close()
