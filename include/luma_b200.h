@@ -124,6 +124,11 @@ typedef struct LumaStats {
 	int64_t kernel_launches;    /* kernels this library launched since create */
 	int64_t halo_bytes_per_step;/* bytes this rank sends per step */
 	int64_t cells;              /* owned cells */
+	/* filled while profiling is on (luma_b200_set_profiling): CUDA events around every launch of the
+	 * dominant kernel (k_step over the interior/all planes), accumulated since profiling was enabled */
+	int64_t step_kernel_launches;
+	double  step_kernel_ms;     /* summed device time of those launches */
+	int64_t step_kernel_cells;  /* summed cells covered by those launches */
 } LumaStats;
 
 #define LUMA_B200_F   1u
@@ -178,6 +183,9 @@ int  luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu);
 int  luma_b200_forces(luma_b200_t *h, double F[3]);
 
 int  luma_b200_stats(luma_b200_t *h, LumaStats *s);
+/* on != 0: bracket each launch of the dominant kernel with CUDA events on its stream (read back by
+ * luma_b200_stats); enabling resets the accumulators.  Off by default. */
+int  luma_b200_set_profiling(luma_b200_t *h, int32_t on);
 int  luma_b200_sync(luma_b200_t *h);
 const char *luma_b200_strerror(int code);
 const char *luma_b200_last_error(luma_b200_t *h);   /* detail of the last non-zero return */

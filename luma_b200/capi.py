@@ -47,7 +47,8 @@ class LumaSyntheticCase(C.Structure):
 class LumaStats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("ms_last_call", C.c_double), ("ms_per_step", C.c_double),
                 ("mlups_last_call", C.c_double), ("kernel_launches", C.c_int64),
-                ("halo_bytes_per_step", C.c_int64), ("cells", C.c_int64)]
+                ("halo_bytes_per_step", C.c_int64), ("cells", C.c_int64),
+                ("step_kernel_launches", C.c_int64), ("step_kernel_ms", C.c_double), ("step_kernel_cells", C.c_int64)]
 
 
 class LumaB200Error(RuntimeError):
@@ -104,8 +105,9 @@ def load(build_if_missing: bool = True):
     L.luma_b200_forces.argtypes = [H, _dp]
     L.luma_b200_stats.argtypes = [H, C.POINTER(LumaStats)]
     L.luma_b200_sync.argtypes = [H]
+    L.luma_b200_set_profiling.argtypes = [H, C.c_int32]
     for nm in ("create", "slab", "comm_unique_id", "comm_init", "upload", "init_synthetic", "step", "download",
-               "download_lattyp", "get_time", "forces", "stats", "sync"):
+               "download_lattyp", "get_time", "forces", "stats", "sync", "set_profiling"):
         getattr(L, "luma_b200_" + nm).restype = C.c_int
     if L.luma_b200_abi_version() != 1:
         raise ImportError("libluma_b200.so ABI version mismatch")

@@ -81,6 +81,9 @@ struct luma_b200
 	bool stepped = false;
 	LumaStats st;
 	std::string err;
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
+	size_t prof_used = 0;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -118,6 +121,30 @@ static void make_constants(LbmConst &C, int Q)
 	if (Q == 19) { C.w[0] = 1.0 / 18.0; C.w[1] = 1.0 / 36.0; C.w[2] = 1.0 / 3.0; }      // src/stdafx.cpp:140-143
 	else { C.w[0] = 1.0 / 9.0; C.w[1] = 1.0 / 36.0; C.w[2] = 4.0 / 9.0; }                // :147-148
 	for (int k = 0; k < 3; ++k) C.wden[k] = C.w[k] / C.den;
+}
+
+static cudaEvent_t prof_event(luma_b200_t *h)
+{
+	if (h->prof_used == h->prof_ev.size())
+	{
+		cudaEvent_t e = nullptr;
+		cudaEventCreate(&e);
+		h->prof_ev.push_back(e);
+	}
+	return h->prof_ev[h->prof_used++];
+}
+
+template <class L>
+static void main_kernel(luma_b200_t *h, const StepArgs &a, bool smag, bool force, int nplanes)
+{
+	if (h->profiling && nplanes > 0) cudaEventRecord(prof_event(h), h->s_main);
+	launch_step<L>(a, smag, force, nplanes, h->s_main, &h->st.kernel_launches);
+	if (h->profiling && nplanes > 0)
+	{
+		cudaEventRecord(prof_event(h), h->s_main);
+		h->st.step_kernel_launches++;
+		h->st.step_kernel_cells += (long long)nplanes * h->MK;
+	}
 }
 
 extern "C" {
@@ -185,6 +212,7 @@ static void free_all(luma_b200_t *h)
 	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_comm) cudaStreamDestroy(h->s_comm);
 }
@@ -528,6 +556,14 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	return LUMA_B200_OK;
 }
 
+int luma_b200_set_profiling(luma_b200_t *h, int32_t on)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	h->profiling = on != 0;
+	h->st.step_kernel_launches = 0; h->st.step_kernel_ms = 0.0; h->st.step_kernel_cells = 0;
+	return LUMA_B200_OK;
+}
+
 int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 {
 	if (!h) return LUMA_B200_EINVAL;
@@ -552,6 +588,7 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	a.smag_coef = 2.0 * LUMA_SQRT2 * (p.csmag * p.csmag) * p.rhoin * h->C.cs2 * h->C.cs2;
 
 	CK(cudaEventRecord(h->ev_t0, h->s_main));
+	h->prof_used = 0;
 	const int owned = p.x_count;
 	for (int s = 0; s < nsteps; ++s)
 	{
@@ -571,8 +608,9 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 
 		if (!h->ghost)
 		{
-			if (h->Q == 19) { launch_bc<D3Q19>(a, smag, force, h->s_main, &h->st.kernel_launches); a.p0 = 0; a.pstep = 1; launch_step<D3Q19>(a, smag, force, h->P, h->s_main, &h->st.kernel_launches); }
-			else { launch_bc<D2Q9>(a, smag, force, h->s_main, &h->st.kernel_launches); a.p0 = 0; a.pstep = 1; launch_step<D2Q9>(a, smag, force, h->P, h->s_main, &h->st.kernel_launches); }
+			a.p0 = 0; a.pstep = 1;
+			if (h->Q == 19) { launch_bc<D3Q19>(a, smag, force, h->s_main, &h->st.kernel_launches); main_kernel<D3Q19>(h, a, smag, force, h->P); }
+			else { launch_bc<D2Q9>(a, smag, force, h->s_main, &h->st.kernel_launches); main_kernel<D2Q9>(h, a, smag, force, h->P); }
 		}
 		else
 		{
@@ -591,8 +629,8 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 			int rc = exchange_populations(h, h->f[h->cur ^ 1], h->s_comm);
 			if (rc) return rc;
 			CK(cudaEventRecord(h->ev_comm, h->s_comm));
-			if (h->Q == 19) launch_step<D3Q19>(in, smag, force, owned - 2, h->s_main, &h->st.kernel_launches);
-			else launch_step<D2Q9>(in, smag, force, owned - 2, h->s_main, &h->st.kernel_launches);
+			if (h->Q == 19) main_kernel<D3Q19>(h, in, smag, force, owned - 2);
+			else main_kernel<D2Q9>(h, in, smag, force, owned - 2);
 		}
 		h->cur ^= 1;
 		++h->t;
@@ -603,6 +641,12 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	CK(cudaStreamSynchronize(h->s_main));
 	float ms = 0.f;
 	CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+	for (size_t e = 0; e + 1 < h->prof_used; e += 2)
+	{
+		float kms = 0.f;
+		CK(cudaEventElapsedTime(&kms, h->prof_ev[e], h->prof_ev[e + 1]));
+		h->st.step_kernel_ms += kms;
+	}
 	h->stepped = true;
 	h->st.steps += nsteps;
 	h->st.ms_last_call = ms;

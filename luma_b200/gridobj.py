@@ -177,6 +177,9 @@ class GridObj:
         capi.check(self._L.luma_b200_stats(self._h, C.byref(s)), self._h)
         return {k: getattr(s, k) for k, _ in s._fields_}
 
+    def set_profiling(self, on: bool = True):
+        capi.check(self._L.luma_b200_set_profiling(self._h, int(on)), self._h)
+
     def sync(self):
         capi.check(self._L.luma_b200_sync(self._h), self._h)
 
