@@ -151,6 +151,21 @@ int  luma_b200_slab(int32_t N, int32_t nranks, int32_t rank, int32_t *x_offset, 
 int  luma_b200_comm_unique_id(void *unique_id_128);
 int  luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128);
 
+/* The per-step exchange of this rank, in issue order (one NCCL group): only the populations that
+ * cross a slab face travel -- c_x = +1 to the +x neighbour (D3Q19 v = 0,6,8,14,17; D2Q9 0,4,6) from
+ * the last owned plane into the neighbour's low ghost plane, c_x = -1 (1,7,9,15,16; 1,5,7) from the
+ * first owned plane into the neighbour's high ghost plane -- each one contiguous run of M*K doubles
+ * of the SoA lattice.  The reference sends all Q populations of every halo site
+ * (src/Mpi_buffer_pack.cpp:72-96).  `plane` is a local plane index (0 = low ghost, 1..x_count owned,
+ * x_count+1 = high ghost).  Host-only; needs no device. */
+typedef struct LumaHaloMsg {
+	int32_t is_send;            /* 1 send, 0 receive */
+	int32_t peer;               /* rank of the other side */
+	int32_t pop;                /* population index v */
+	int32_t plane;              /* local plane read (send) or written (receive) */
+} LumaHaloMsg;
+int  luma_b200_halo_plan(const LumaCaseParams *p, LumaHaloMsg *msgs, int32_t capacity, int32_t *count);
+
 /* ---- state in: everything LBM_multi_opt reads (GridObj fields, inc/GridObj.h:74-125).
  *      Arrays cover this rank's owned planes, preceded/followed by `halo` extra x-planes
  *      (0 for the serial build, 1 for LUMA's MPI build whose local arrays carry recv layers,
@@ -187,6 +202,9 @@ int  luma_b200_stats(luma_b200_t *h, LumaStats *s);
  * luma_b200_stats); enabling resets the accumulators.  Off by default. */
 int  luma_b200_set_profiling(luma_b200_t *h, int32_t on);
 int  luma_b200_sync(luma_b200_t *h);
+/* device self-test of the constant-divisor division used for x/cs^2 and x/(2cs^4) (lattice.cuh,
+ * tests/test_constdiv_exact.py): compares it with IEEE `/` on n pseudo-random operands. */
+int  luma_b200_selftest_div_const(int32_t device, int64_t n, uint64_t seed, int64_t *mismatches);
 const char *luma_b200_strerror(int code);
 const char *luma_b200_last_error(luma_b200_t *h);   /* detail of the last non-zero return */
 int  luma_b200_abi_version(void);

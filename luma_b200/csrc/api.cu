@@ -333,21 +333,33 @@ static int edge_pops(int Q, int sign, int out[8])
 
 // the exchange step: only the populations that cross the slab face, straight from / into the SoA
 // lattice (each is one contiguous M*K run), ring topology (MPI_Cart_create periodic, MpiManager.cpp:112-136)
+static int build_halo_plan(const LumaCaseParams &p, std::vector<LumaHaloMsg> &plan)
+{
+	plan.clear();
+	if (p.nranks < 2) return 0;
+	const int n = p.nranks, right = (p.rank + 1) % n, left = (p.rank - 1 + n) % n;
+	int plus[8], minus[8];
+	const int np = edge_pops(p.num_vels, +1, plus), nm = edge_pops(p.num_vels, -1, minus);
+	const int P = p.x_count + 2;
+	for (int a = 0; a < np; ++a) plan.push_back({ 1, right, plus[a], P - 2 });
+	for (int a = 0; a < np; ++a) plan.push_back({ 0, left, plus[a], 0 });
+	for (int a = 0; a < nm; ++a) plan.push_back({ 1, left, minus[a], 1 });
+	for (int a = 0; a < nm; ++a) plan.push_back({ 0, right, minus[a], P - 1 });
+	return (int)plan.size();
+}
+
 static int exchange_populations(luma_b200_t *h, double *lat, cudaStream_t s)
 {
-	const int n = h->p.nranks, right = (h->p.rank + 1) % n, left = (h->p.rank - 1 + n) % n;
-	int plus[8], minus[8];
-	const int np = edge_pops(h->Q, +1, plus), nm = edge_pops(h->Q, -1, minus);
+	std::vector<LumaHaloMsg> plan;
+	build_halo_plan(h->p, plan);
 	const size_t cnt = (size_t)h->MK;
 	NK(g_nccl.GroupStart());
-	for (int a = 0; a < np; ++a)
-		NK(g_nccl.Send(lat + (long long)plus[a] * h->stride + (long long)(h->P - 2) * h->MK, cnt, ncclFloat64, right, h->comm, s));
-	for (int a = 0; a < np; ++a)
-		NK(g_nccl.Recv(lat + (long long)plus[a] * h->stride, cnt, ncclFloat64, left, h->comm, s));
-	for (int a = 0; a < nm; ++a)
-		NK(g_nccl.Send(lat + (long long)minus[a] * h->stride + h->MK, cnt, ncclFloat64, left, h->comm, s));
-	for (int a = 0; a < nm; ++a)
-		NK(g_nccl.Recv(lat + (long long)minus[a] * h->stride + (long long)(h->P - 1) * h->MK, cnt, ncclFloat64, right, h->comm, s));
+	for (const LumaHaloMsg &m : plan)
+	{
+		double *ptr = lat + (long long)m.pop * h->stride + (long long)m.plane * h->MK;
+		if (m.is_send) NK(g_nccl.Send(ptr, cnt, ncclFloat64, m.peer, h->comm, s));
+		else NK(g_nccl.Recv(ptr, cnt, ncclFloat64, m.peer, h->comm, s));
+	}
 	NK(g_nccl.GroupEnd());
 	return LUMA_B200_OK;
 }
@@ -743,6 +755,37 @@ int luma_b200_stats(luma_b200_t *h, LumaStats *s)
 {
 	if (!h || !s) return LUMA_B200_EINVAL;
 	*s = h->st;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_halo_plan(const LumaCaseParams *p, LumaHaloMsg *msgs, int32_t capacity, int32_t *count)
+{
+	if (!p || !count || p->struct_size != sizeof(LumaCaseParams)) return LUMA_B200_EINVAL;
+	if (!((p->dims == 3 && p->num_vels == 19) || (p->dims == 2 && p->num_vels == 9))) return LUMA_B200_EINVAL;
+	if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks || p->x_count < 1) return LUMA_B200_EINVAL;
+	std::vector<LumaHaloMsg> plan;
+	const int n = build_halo_plan(*p, plan);
+	*count = n;
+	if (!msgs) return LUMA_B200_OK;
+	if (capacity < n) return LUMA_B200_EINVAL;
+	for (int i = 0; i < n; ++i) msgs[i] = plan[(size_t)i];
+	return LUMA_B200_OK;
+}
+
+int luma_b200_selftest_div_const(int32_t device, int64_t n, uint64_t seed, int64_t *mismatches)
+{
+	if (!mismatches || n < 0) return LUMA_B200_EINVAL;
+	if (cudaSetDevice(device) != cudaSuccess) return LUMA_B200_ECUDA;
+	LbmConst C;
+	make_constants(C, 19);
+	unsigned long long *d = nullptr, hcount = 0;
+	if (cudaMalloc(&d, sizeof(*d)) != cudaSuccess) return LUMA_B200_ENOMEM;
+	cudaMemset(d, 0, sizeof(*d));
+	launch_selftest_div(C, (unsigned long long)seed, (long long)n, d, 0);
+	const cudaError_t e = cudaMemcpy(&hcount, d, sizeof(hcount), cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return LUMA_B200_ECUDA;
+	*mismatches = (int64_t)hcount;
 	return LUMA_B200_OK;
 }
 

@@ -551,6 +551,32 @@ template <class L> int launch_momex(const double *f_prev, const uint8_t *types, 
 	return blocks;
 }
 
+// ------------------------------------------------------------------------------------------------
+// self-test: div_const against IEEE division on pseudo-random operands (all binades the step sees)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_selftest_div(const LbmConst C, unsigned long long seed, long long n, unsigned long long *mismatches)
+{
+	unsigned long long bad = 0;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+	{
+		unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);   // splitmix64
+		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+		z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+		z ^= z >> 31;
+		const unsigned long long mant = z & 0xFFFFFFFFFFFFFull;
+		const unsigned long long expo = 1023ull - 90ull + ((z >> 52) % 100ull);                // 2^-90 .. 2^9
+		const unsigned long long sign = (z >> 63) << 63;
+		const double a = __longlong_as_double((long long)(sign | (expo << 52) | mant));
+		if (div_const(a, C.cs2, C.inv_cs2) != a / C.cs2) ++bad;
+		if (div_const(a, C.den, C.inv_den) != a / C.den) ++bad;
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+void launch_selftest_div(const LbmConst &C, unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t s)
+{
+	k_selftest_div<<<148 * 8, 256, 0, s>>>(C, seed, n, mismatches);
+}
+
 // explicit instantiations
 #define LUMA_INST(L) \
 	template void launch_step<L>(const StepArgs &, bool, bool, int, cudaStream_t, int64_t *); \

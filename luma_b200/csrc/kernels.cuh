@@ -76,6 +76,7 @@ void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int D
 void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int D, long long first_cell, long long ncells, cudaStream_t s);
 void launch_types_from_i32(const int32_t *in, uint8_t *out, long long n, cudaStream_t s);
 void launch_types_to_i32(const uint8_t *in, int32_t *out, long long n, cudaStream_t s);
+void launch_selftest_div(const LbmConst &C, unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t s);
 // momentum exchange: per-block partial sums [nblocks][3]; returns nblocks
 template <class L> int launch_momex(const double *f_prev, const uint8_t *types, long long stride, int P, int M, int K,
 	int p_begin, int p_end, int x_first, int N, double *partials, int max_blocks, cudaStream_t s);

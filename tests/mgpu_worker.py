@@ -1,0 +1,69 @@
+"""Worker of tests/test_gpu_multi.py: run under torch.distributed.run, one rank per GPU.
+Every rank steps its x-slab on its GPU and compares it bit-for-bit with the same planes of the
+serial oracle (the reference's MPI result equals its serial result on core sites)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import luma_b200  # noqa: E402
+from luma_b200 import capi, ring  # noqa: E402
+from oracle import port  # noqa: E402
+from oracle.cases import CASES  # noqa: E402
+from util import defs_from_case, first_diff  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    uid = ring.broadcast_unique_id(dist, rank)
+    names = sys.argv[1].split(",")
+    for name in names:
+        case = CASES[name]
+        defs = defs_from_case(case)
+        ref = port.PortGrid(case)
+        Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
+        for mode in ("device_init", "upload"):
+            g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
+            x0, cnt = g.x_offset, g.x_count
+            ref = port.PortGrid(case)
+            if mode == "device_init":
+                g.LBM_initGrid()
+            else:
+                sl = slice(x0 * MK, (x0 + cnt) * MK)
+                g.upload(ref.f.reshape(-1, Q)[sl], ref.rho[sl], ref.u.reshape(-1, D)[sl], ref.lattyp[sl],
+                         ref.uin(0), ref.uin(1), ref.uin(2))
+            done = 0
+            for s in (1, 2, 10, 50):
+                g.LBM_multi_opt(s - done)
+                ref.step(s - done)
+                done = s
+                got = g.download()
+                sl = slice(x0 * MK, (x0 + cnt) * MK)
+                for nm, width in (("f", Q), ("rho", 1), ("u", D)):
+                    a = got[nm].reshape(-1, width)
+                    b = getattr(ref, nm).reshape(-1, width)[sl]
+                    assert np.array_equal(a, b), "rank %d %s %s t=%d %s: %s" % (rank, name, mode, s, nm, first_diff(a.ravel(), b.ravel()))
+            if case.ld_out:
+                F = torch.tensor(g.computeLiftDrag(), dtype=torch.float64, device="cuda")
+                dist.all_reduce(F)
+                Fr = ref.force
+                assert np.all(np.abs(F.cpu().numpy() - Fr) <= 1e-10 * max(1.0, np.abs(Fr).max())), (F, Fr)
+            st = g.stats()
+            assert st["halo_bytes_per_step"] == 2 * (5 if Q == 19 else 3) * MK * 8
+            g.close(); ref.close()
+        dist.barrier()
+        if rank == 0:
+            print("mgpu ok: %s on %d GPUs (device_init + upload), bit-identical to the serial oracle" % (name, world), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+"""Multi-GPU parity (needs >= 2 GPUs, skipped otherwise): x-slabs over NCCL must reproduce the serial
+reference bit-for-bit on every rank's planes."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slabs_match_serial_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    # cases whose x extent leaves >= 4 planes per rank and whose BC extrapolation stays inside a slab
+    names = "chan3d,cyl3d,cav3d_32,chan2d,cyl2d" if world <= 4 else "chan3d,cyl3d,chan2d,cyl2d"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29610 + world), os.path.join(HERE, "mgpu_worker.py"), names]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    out = r.stdout.decode()
+    assert r.returncode == 0, out[-4000:]
+    assert out.count("mgpu ok") == len(names.split(",")), out[-4000:]

@@ -83,6 +83,15 @@ def test_device_init_path_bitwise_vs_oracle(name):
     g.close(); ref.close()
 
 
+def test_div_const_equals_ieee_division_on_device():
+    """2 x 2^31 random operands on the GPU: the 3-operation constant division must equal `/` bit for bit
+    (the proof by enumeration is tests/test_constdiv_exact.py)."""
+    import ctypes as C
+    bad = C.c_int64(-1)
+    capi.check(capi.load().luma_b200_selftest_div_const(0, 1 << 31, 20261017, C.byref(bad)))
+    assert bad.value == 0
+
+
 def test_single_step_calls_equal_batched_calls():
     case = CASES["cyl2d"]
     a = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()

@@ -1,0 +1,101 @@
+"""World-size-2 (and 3) `gloo` tests of the N>1 host logic, on CPU: slab decomposition, ring
+bootstrap and the halo plan the library issues every step (luma_b200_halo_plan), replayed on host
+tensors and checked against the global periodic lattice of the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from luma_b200 import capi, ring
+from oracle import port
+from oracle.cases import CASES
+from util import defs_from_case
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port_no, name, q):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port_no)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        case = CASES[name]
+        defs = defs_from_case(case)
+        # bootstrap: the 128-byte id travels from rank 0 to everyone (id factory injected: no NCCL on CPU boxes)
+        uid = ring.broadcast_unique_id(dist, rank, make_id=lambda: bytes(range(128)))
+        assert uid == bytes(range(128))
+
+        # every rank holds the oracle's global state (stand-in for LUMA's per-rank arrays)
+        g = port.PortGrid(case)
+        g.step(3)
+        Q, N, M, K = case.Q, case.N, case.M, case.K
+        f = g.f.reshape(N, M * K, Q)                       # AoS -> [x, site-in-plane, v]
+        x0, cnt = capi.slab(N, world, rank)
+        # local SoA lattice with ghost planes, owned planes filled, ghosts poisoned
+        lat = torch.full((Q, cnt + 2, M * K), float("nan"), dtype=torch.float64)
+        lat[:, 1:cnt + 1, :] = torch.from_numpy(np.ascontiguousarray(f[x0:x0 + cnt].transpose(2, 0, 1)))
+        plan = ring.halo_plan(defs, rank, world)
+        ring.execute_plan_on_host(dist, plan, lat)
+
+        cx = [(1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 0, 0, 1, -1, -1, 1, 0), (1, -1, 0, 0, 1, -1, 1, -1, 0)][Q == 9]
+        lo, hi = (x0 - 1) % N, (x0 + cnt) % N
+        for v in range(Q):
+            if cx[v] == 1:      # pulled from x-1: must be in the low ghost plane
+                assert np.array_equal(lat[v, 0].numpy(), f[lo, :, v]), ("low ghost", v)
+                assert np.isnan(lat[v, cnt + 1].numpy()).all()
+            elif cx[v] == -1:   # pulled from x+1: high ghost plane
+                assert np.array_equal(lat[v, cnt + 1].numpy(), f[hi, :, v]), ("high ghost", v)
+                assert np.isnan(lat[v, 0].numpy()).all()
+            else:               # never exchanged
+                assert np.isnan(lat[v, 0].numpy()).all() and np.isnan(lat[v, cnt + 1].numpy()).all()
+        # bytes on the wire: 5 (3) populations per face instead of the reference's 19 (9)
+        sends = [m for m in plan if m["is_send"]]
+        assert len(sends) == (10 if Q == 19 else 6)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:   # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+
+
+@pytest.mark.parametrize("name,world", [("chan3d", 2), ("chan2d", 2), ("cav3d_32", 3)])
+def test_halo_plan_over_gloo(name, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_plan_is_empty_for_a_single_rank_and_symmetric_otherwise():
+    defs = defs_from_case(CASES["chan3d"])
+    assert ring.halo_plan(defs, 0, 1) == []
+    for world in (2, 4, 8):
+        plans = [ring.halo_plan(defs, r, world) for r in range(world)]
+        for r, plan in enumerate(plans):
+            for m in plan:
+                if m["is_send"]:
+                    # the peer must post the matching receive of the same population
+                    assert any((not o["is_send"]) and o["peer"] == r and o["pop"] == m["pop"] for o in plans[m["peer"]])
+        # per peer, sends and the peer's receives are issued in the same population order (NCCL matches in order)
+        for r in range(world):
+            for peer in set(m["peer"] for m in plans[r]):
+                s = [m["pop"] for m in plans[r] if m["is_send"] and m["peer"] == peer]
+                rcv = [m["pop"] for m in plans[peer] if (not m["is_send"]) and m["peer"] == r]
+                assert s == rcv, (world, r, peer)
