@@ -146,8 +146,8 @@ int  luma_b200_slab(int32_t N, int32_t nranks, int32_t rank, int32_t *x_offset, 
 
 /* ---- multi-GPU: attach this process to the ring.  unique_id = the 128 bytes of an ncclUniqueId
  *      created by rank 0 (luma_b200_comm_unique_id) and broadcast by the host (MPI_Bcast in a
- *      LUMA MPI build, torch.distributed in bench.py).  Replaces MpiManager::mpi_init /
- *      mpi_buffer_size for level 0. ---- */
+ *      LUMA MPI build, torch.distributed in bench.py).  One unique id per handle (an id bootstraps
+ *      exactly one communicator).  Replaces MpiManager::mpi_init / mpi_buffer_size for level 0. ---- */
 int  luma_b200_comm_unique_id(void *unique_id_128);
 int  luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128);
 

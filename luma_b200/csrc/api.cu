@@ -254,7 +254,12 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	if (ndev < 1 || p->device < 0 || p->device >= ndev) FAIL(LUMA_B200_ECUDA, "no such CUDA device");
 	CK(cudaSetDevice(p->device));
 	CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
-	CK(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+	{
+		// the exchange must not queue behind the interior kernel's 65k blocks: highest priority for its stream
+		int lo = 0, hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CK(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi));
+	}
 	CK(cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
 	CK(cudaEventCreate(&h->ev_t0));

@@ -23,7 +23,6 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = ring.broadcast_unique_id(dist, rank)
     names = sys.argv[1].split(",")
     for name in names:
         case = CASES[name]
@@ -31,6 +30,7 @@ def main():
         ref = port.PortGrid(case)
         Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
         for mode in ("device_init", "upload"):
+            uid = ring.broadcast_unique_id(dist, rank)      # one ncclUniqueId per communicator / handle
             g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
             x0, cnt = g.x_offset, g.x_count
             ref = port.PortGrid(case)
