@@ -1,0 +1,173 @@
+/* GridObj_ops_lbm_b200.cpp -- the drop-in: GridObj::LBM_multi_opt forwarding to libluma_b200.so.
+ *
+ * Build it INTO LUMA (it includes LUMA's own headers and is a GridObj member, so it can read the
+ * private fields f, u, rho, ux_in ..., inc/GridObj.h:74-103) and compile LUMA's
+ * src/GridObj_ops_lbm_optimised.cpp with  -DLBM_multi_opt=LBM_multi_opt_cpu  so that its CPU body
+ * (src/GridObj_ops_lbm_optimised.cpp:36-193) keeps a different name while every other function of that
+ * file (_LBM_equilibrium_opt is needed by LBM_initGrid and io_restart) stays linked.  Nothing else
+ * in LUMA changes: inc/definitions.h still fixes the case at compile time, GridObj/GridManager/
+ * ObjectManager build the grid, label walls and bodies, and the IO code reads the same host arrays.
+ *
+ *   first call : LumaCaseParams from the macros + members, wall descriptors of the velocity/pressure
+ *                sites from GridUtils::isWithinDomainWall, luma_b200_upload of f, rho, u, LatTyp.
+ *   every call : luma_b200_step(1); GridObj::t, omega, nu follow the device.
+ *   host sync  : rho, u (and f when a restart file is due) are downloaded into the GridObj arrays
+ *                whenever main() is about to read them -- t % L_GRID_OUT_FREQ, L_PROBE_OUT_FREQ,
+ *                L_EXTRA_OUT_FREQ, L_RESTART_OUT_FREQ (src/main_lbm.cpp:449-561) -- or on demand with
+ *                LBM_multi_opt(LUMA_B200_SYNC_HOST).
+ *
+ * Serial build (L_BUILD_FOR_MPI undefined): one process, one GPU.  MPI build: one rank per GPU,
+ * L_MPI_XCORES = ranks, L_MPI_YCORES = L_MPI_ZCORES = 1; the ncclUniqueId is broadcast with MPI_Bcast
+ * and mpi_communicate is NOT called for level 0 (the library exchanges the slab faces itself).
+ */
+#include "LUMA/inc/stdafx.h"
+#include "LUMA/inc/GridObj.h"
+#include "LUMA/inc/GridUtils.h"
+#ifdef L_BUILD_FOR_MPI
+#include "LUMA/inc/MpiManager.h"
+#endif
+
+#include "luma_b200.h"
+
+#include <cstdlib>
+#include <vector>
+
+#ifndef LUMA_B200_SYNC_HOST
+#define LUMA_B200_SYNC_HOST (-1)      /* LBM_multi_opt(LUMA_B200_SYNC_HOST): download f, rho, u; no time step */
+#endif
+
+static_assert(sizeof(eType) == sizeof(int32_t), "LatTyp is handed over as int32");
+
+namespace
+{
+	luma_b200_t *g_dev = nullptr;
+
+	void check(int rc, const char *what)
+	{
+		if (rc == LUMA_B200_OK) return;
+		std::string msg = std::string("luma_b200 ") + what + ": " + luma_b200_strerror(rc);
+		if (g_dev) msg += std::string(" [") + luma_b200_last_error(g_dev) + "]";
+		L_ERROR(msg, GridUtils::logfile);      /* log, MPI_Finalize, exit -- inc/stdafx.h:135-149 */
+	}
+}
+
+void GridObj::LBM_multi_opt(int subcycle)
+{
+	if (level != 0)
+		L_ERROR("luma_b200 accelerates level 0 only (L_NUM_LEVELS must be 0)", GridUtils::logfile);
+
+	const int halo =
+#ifdef L_BUILD_FOR_MPI
+		1;      /* local arrays carry one recv layer each side in x, src/MpiManager.cpp:277-282 */
+#else
+		0;
+#endif
+
+	if (!g_dev)
+	{
+		LumaCaseParams p;
+		luma_b200_default_params(&p);
+		p.dims = L_DIMS;
+		p.num_vels = L_NUM_VELS;
+		p.N = L_N; p.M = L_M; p.K = L_K;
+#ifdef L_BUILD_FOR_MPI
+		MpiManager *mpim = MpiManager::getInstance();
+		if (L_MPI_YCORES != 1 || L_MPI_ZCORES != 1)
+			L_ERROR("luma_b200 decomposes along x only: set L_MPI_YCORES = L_MPI_ZCORES = 1", GridUtils::logfile);
+		p.rank = mpim->my_rank; p.nranks = mpim->num_ranks;
+#endif
+		check(luma_b200_slab(p.N, p.nranks, p.rank, &p.x_offset, &p.x_count), "slab");
+		if (p.x_count + 2 * halo != N_lim)
+			L_ERROR("luma_b200: slab width differs from the host decomposition (use the uniform decomposition)", GridUtils::logfile);
+		const char *dev = getenv("LUMA_B200_DEVICE");
+		p.device = dev ? atoi(dev) : p.rank;
+#ifdef L_REGULARISED_BOUNDARIES
+		p.regularised = 1;
+#else
+		p.regularised = 0;
+#endif
+#ifdef L_USE_BGKSMAG
+		p.bgksmag = 1;
+#endif
+		p.csmag = L_CSMAG;
+#ifdef L_GRAVITY_ON
+		p.gravity_on = 1;
+#endif
+		p.gravity_dir = static_cast<int>(L_GRAVITY_DIRECTION);
+		p.gravity = gravity;
+		p.rhoin = L_RHOIN;
+		p.rho_out = L_RHOIN;
+#ifdef L_PRESSURE_DELTA
+		p.rho_out += GridUnits::pd2dlbm(L_PRESSURE_DELTA, this);      /* optimised.cpp:343-345 */
+#endif
+		p.dt = dt; p.dh = dh;
+		p.omega = omega;
+#ifdef L_VELOCITY_RAMP
+		p.velocity_ramp_on = 1; p.velocity_ramp = L_VELOCITY_RAMP;
+#endif
+#ifdef L_REYNOLDS_RAMP
+		p.reynolds_ramp_on = 1; p.reynolds_ramp = L_REYNOLDS_RAMP;
+#endif
+		p.re = static_cast<double>(L_RE);
+		p.t = t;
+#if defined(L_USE_KBC_COLLISION) || defined(L_IBM_ON) || (L_NUM_LEVELS != 0)
+		L_ERROR("luma_b200: KBC, IBM and grid refinement are outside the accelerated path", GridUtils::logfile);
+#endif
+		check(luma_b200_create(&g_dev, &p), "create");
+#ifdef L_BUILD_FOR_MPI
+		{
+			char id[128];
+			if (p.rank == 0) check(luma_b200_comm_unique_id(id), "comm_unique_id");
+			MPI_Bcast(id, 128, MPI_CHAR, 0, mpim->world_comm);
+			check(luma_b200_comm_init(g_dev, id), "comm_init");
+		}
+#endif
+		/* wall descriptors exactly as _LBM_regularised_opt would obtain them (optimised.cpp:334) */
+		std::vector<LumaSiteBC> bc;
+		std::vector<int> nv(3, 0);
+		for (int i = 0; i < N_lim; ++i) for (int j = 0; j < M_lim; ++j) for (int k = 0; k < K_lim; ++k)
+		{
+			const int64_t id = k + (int64_t)j * K_lim + (int64_t)i * K_lim * M_lim;
+			const eType ty = LatTyp[id];
+			if (ty != eVelocity && ty != ePressure) continue;
+			eCartesianDirection nd = eXDirection; unsigned int ec = 0;
+			nv[0] = nv[1] = nv[2] = 0;
+			LumaSiteBC s = { id, 0, 0, { 0, 0, 0 }, { 0, 0, 0 } };
+			if (GridUtils::isWithinDomainWall(XPos[i], YPos[j], ZPos[k], &nv, &nd, &ec))
+			{
+				s.edge_count = (int8_t)ec; s.normal_dir = (int8_t)nd;
+				s.normal[0] = (int8_t)nv[0]; s.normal[1] = (int8_t)nv[1]; s.normal[2] = (int8_t)nv[2];
+			}
+			bc.push_back(s);
+		}
+		check(luma_b200_upload(g_dev, halo, &f[0], &rho[0], &u[0], reinterpret_cast<const int32_t *>(&LatTyp[0]),
+			bc.empty() ? nullptr : &bc[0], bc.size(), &ux_in[0], &uy_in[0], &uz_in[0]), "upload");
+	}
+
+	if (subcycle == LUMA_B200_SYNC_HOST)
+	{
+		check(luma_b200_download(g_dev, halo, LUMA_B200_F | LUMA_B200_RHO | LUMA_B200_U, &f[0], &rho[0], &u[0]), "download");
+		return;
+	}
+
+	clock_t t_start = clock();
+	check(luma_b200_step(g_dev, 1), "step");
+	check(luma_b200_get_time(g_dev, &t, &omega, &nu), "get_time");      /* ++t, _LBM_updateReynolds (optimised.cpp:39-42,:170) */
+
+	/* host arrays are refreshed exactly when main() reads them (src/main_lbm.cpp:449-561) */
+	unsigned what = 0;
+	if (t % L_GRID_OUT_FREQ == 0 || t % L_PROBE_OUT_FREQ == 0 || t % L_EXTRA_OUT_FREQ == 0) what |= LUMA_B200_RHO | LUMA_B200_U;
+	if (t % L_RESTART_OUT_FREQ == 0) what |= LUMA_B200_F | LUMA_B200_RHO | LUMA_B200_U;
+#ifdef L_LD_OUT
+	/* ObjectManager::computeLiftDrag accumulates into private members of ObjectManager; a LUMA build
+	 * that writes lift/drag adds `friend void GridObj::LBM_multi_opt(int)` there or reads
+	 * luma_b200_forces() in io_writeForcesOnObjects -- see INTEGRATION.md */
+#endif
+	if (what) check(luma_b200_download(g_dev, halo, what, &f[0], &rho[0], &u[0]), "download");
+
+	/* the reference's running average of the step time (optimised.cpp:172-183) */
+	const double secs = static_cast<double>(clock() - t_start) / CLOCKS_PER_SEC;
+	timeav_timestep *= (t - 1);
+	timeav_timestep += secs;
+	timeav_timestep /= t;
+}

@@ -11,6 +11,10 @@
  * GridManager::getInstance() -> new GridObj(0) -> setGridHierarchy ->
  * ObjectManager::getInstance(Grids) -> (body labelling) -> time loop :422-572.
  *
+ * With -DLUMA_DROPIN the same driver is linked against luma_b200/host/GridObj_ops_lbm_b200.cpp
+ * instead of the reference's CPU LBM_multi_opt (oracle/Makefile target `dropin`): the unmodified LUMA
+ * host then steps on the GPU -- the drop-in demonstration checked by tests/test_gpu_dropin.py.
+ *
  * usage:  luma_ref_<case> dump  <outdir> <step[,step...]>
  *         luma_ref_<case> bench <warmup> <steps>
  */
@@ -173,6 +177,9 @@ int main(int argc, char **argv)
 			Grids->LBM_multi_opt();                          /* main_lbm.cpp:441 */
 			if (next < snaps.size() && Grids->t == snaps[next])
 			{
+#ifdef LUMA_DROPIN
+				Grids->LBM_multi_opt(-1);                    /* LUMA_B200_SYNC_HOST: refresh the host arrays */
+#endif
 				Grids->io_lite((double)Grids->t, outdir + "/t" + std::to_string(Grids->t));
 				++next;
 			}
