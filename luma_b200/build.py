@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libluma_b200.so")
+LIB = os.environ.get("LUMA_B200_LIB") or os.path.join(HERE, "libluma_b200.so")
 STAMP = LIB + ".srchash"
 SOURCES = ["kernels.cu", "api.cu"]
 HEADERS = ["lattice.cuh", "kernels.cuh", os.path.join("..", "..", "include", "luma_b200.h")]
@@ -42,14 +42,29 @@ def _src_hash() -> str:
 
 
 def is_current() -> bool:
+    if os.environ.get("LUMA_B200_LIB"):
+        return os.path.exists(LIB)
     if not (os.path.exists(LIB) and os.path.exists(STAMP)):
         return False
     with open(STAMP) as fh:
         return fh.read().strip() == _src_hash()
 
 
+def build_variant(tag: str, defines) -> str:
+    """Development aid: an extra library built with -D tuning knobs (kernels.cu), e.g.
+    build_variant("t128", ["-DLUMA_STEP_THREADS=128"]) -> luma_b200/libluma_b200_t128.so."""
+    nvcc = _nvcc()
+    out = os.path.join(HERE, "libluma_b200_%s.so" % tag)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run([nvcc] + NVCC_FLAGS + list(defines) + ["-I", "/usr/include", "-shared", "-o", out] + srcs + ["-ldl"],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if the sources changed; returns its path."""
+    if os.environ.get("LUMA_B200_LIB"):
+        return LIB
     if not force and is_current():
         return LIB
     nvcc = _nvcc()

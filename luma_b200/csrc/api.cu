@@ -597,6 +597,13 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	a.P = h->P; a.M = p.M; a.K = p.K; a.MK = (unsigned)h->MK;
 	a.wrap_x = h->ghost ? 0 : 1;
 	a.C = h->C;
+	for (int v = 0; v < h->Q; ++v)
+	{
+		const int cx = (h->Q == 19) ? D3Q19::c(v, 0) : D2Q9::c(v, 0);
+		const int cy = (h->Q == 19) ? D3Q19::c(v, 1) : D2Q9::c(v, 1);
+		const int cz = (h->Q == 19) ? D3Q19::c(v, 2) : D2Q9::c(v, 2);
+		a.off_pull[v] = 8LL * ((long long)v * h->stride - ((long long)cx * h->MK + (long long)cy * p.K + cz));
+	}
 	a.bc_list = h->bc_list; a.n_bc = h->n_bc; a.uin = h->uin;
 	a.rho_out = p.rho_out;
 	// force_xyz = rho_init * gravity * refinement_ratio along L_GRAVITY_DIRECTION (init_grids.cpp:296-297)

@@ -12,7 +12,45 @@
 
 namespace luma {
 
-constexpr int STEP_THREADS = 256;
+// tuning knobs (defaults are the measured best, profiles/r01_variants.txt)
+#ifndef LUMA_STEP_THREADS
+#define LUMA_STEP_THREADS 128
+#endif
+#ifndef LUMA_MIN_BLOCKS
+#define LUMA_MIN_BLOCKS 6
+#endif
+#ifndef LUMA_LOAD_MODE
+#define LUMA_LOAD_MODE 0      /* 0 ld.global.nc (__ldg), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate, 3 plain */
+#endif
+#ifndef LUMA_STORE_MODE
+#define LUMA_STORE_MODE 0     /* 0 plain, 1 st.global.cs, 2 st.global.L1::no_allocate */
+#endif
+constexpr int STEP_THREADS = LUMA_STEP_THREADS;
+
+__device__ __forceinline__ double load_pop(const double *p)
+{
+#if LUMA_LOAD_MODE == 0
+	return __ldg(p);
+#elif LUMA_LOAD_MODE == 1
+	return __ldcs(p);
+#elif LUMA_LOAD_MODE == 2
+	double v;
+	asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+	return v;
+#else
+	return *p;
+#endif
+}
+__device__ __forceinline__ void store_pop(double *p, double v)
+{
+#if LUMA_STORE_MODE == 0
+	*p = v;
+#elif LUMA_STORE_MODE == 1
+	__stcs(p, v);
+#else
+	asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------
 // pull-stream of one site, GridObj::_LBM_stream_opt (optimised.cpp:206-297): population v comes
@@ -23,6 +61,16 @@ template <class L>
 __device__ __forceinline__ void pull_populations(const StepArgs &a, const int p, const unsigned r, const long long id,
 	const uint32_t w, double (&f)[L::Q])
 {
+	const double *base = a.fin + id;
+	const bool x_wraps = a.wrap_x && (p == 0 || p == a.P - 1);
+	if ((w & (CW_LINKS | CW_EDGE)) == 0 && !x_wraps)
+	{
+		// interior site with fluid neighbours only (the overwhelmingly common case): kernel-uniform offsets
+		const char *pb = reinterpret_cast<const char *>(base);
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v) f[v] = load_pop(reinterpret_cast<const double *>(pb + a.off_pull[v]));
+		return;
+	}
 	long long xm = -(long long)a.MK, xp = (long long)a.MK;      // offsets to x-1 / x+1
 	if (a.wrap_x)
 	{
@@ -41,7 +89,6 @@ __device__ __forceinline__ void pull_populations(const StepArgs &a, const int p,
 			if (k == (unsigned)a.K - 1) zp = -(long long)(a.K - 1);
 		}
 	}
-	const double *base = a.fin + id;
 #pragma unroll
 	for (int v = 0; v < L::Q; ++v)
 	{
@@ -55,7 +102,7 @@ __device__ __forceinline__ void pull_populations(const StepArgs &a, const int p,
 			const long long off_bb = (long long)opposite<L>(v) * a.stride;
 			if ((w >> v) & 1u) off = off_bb;
 		}
-		f[v] = __ldg(base + off);
+		f[v] = load_pop(base + off);
 	}
 }
 
@@ -78,16 +125,17 @@ __device__ __forceinline__ void collide(const StepArgs &a, const double (&u)[3],
 template <class L>
 __device__ __forceinline__ void store_populations(const StepArgs &a, const long long id, const double (&f)[L::Q])
 {
-	double *base = a.fout + id;
+	char *pb = reinterpret_cast<char *>(a.fout + id);
+	const long long sb = a.stride * (long long)sizeof(double);
 #pragma unroll
-	for (int v = 0; v < L::Q; ++v) base[(long long)v * a.stride] = f[v];
+	for (int v = 0; v < L::Q; ++v) store_pop(reinterpret_cast<double *>(pb + (long long)v * sb), f[v]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
 // ------------------------------------------------------------------------------------------------
 template <class L, bool SMAG, bool FORCE>
-__global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs a)
+__global__ void __launch_bounds__(STEP_THREADS, LUMA_MIN_BLOCKS) k_step(const StepArgs a)
 {
 	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
 	if (r >= a.MK) return;

@@ -14,6 +14,7 @@ struct StepArgs
 	double *rho;              // [cells]
 	double *u;                // SoA [D][stride]
 	long long stride;         // elements between populations (>= cells, multiple of 16)
+	long long off_pull[19];   // BYTE offset 8*(v*stride - (cx*M*K + cy*K + cz)): where population v is pulled from (no wrap, no bounce-back)
 	int P, M, K;              // local planes (incl. ghost planes when !wrap_x), rows, columns
 	unsigned MK;              // M*K
 	int wrap_x;               // 1: periodic wrap inside the array (single rank); 0: ghost planes 0 and P-1
