@@ -129,7 +129,6 @@ typedef struct LumaStats {
 	int64_t step_kernel_launches;
 	double  step_kernel_ms;     /* summed device time of those launches */
 	int64_t step_kernel_cells;  /* summed lattice updates covered by those launches */
-	int64_t fused_steps;        /* steps executed two-per-sweep (luma_b200_set_temporal_blocking) */
 } LumaStats;
 
 #define LUMA_B200_F   1u
@@ -199,14 +198,6 @@ int  luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu);
 int  luma_b200_forces(luma_b200_t *h, double F[3]);
 
 int  luma_b200_stats(luma_b200_t *h, LumaStats *s);
-/* Two time steps per sweep (temporal blocking through the L2): the sweep reads the lattice once and writes
- * it once per TWO steps; the intermediate time level lives in a ring of row strips that stays in L2.
- * Results are bit-identical to the one-step path.  mode 1 = use it when the case is eligible (single rank,
- * boundary sites limited to velocity faces whose normal lies in the plane); otherwise, and for the last
- * step of every call, the one-step kernels run.  rows_per_strip / lag / ring_slots = 0 pick defaults.
- * The default mode comes from the environment variable LUMA_B200_TB (0 when unset). */
-int  luma_b200_set_temporal_blocking(luma_b200_t *h, int32_t mode, int32_t rows_per_strip, int32_t lag, int32_t ring_slots);
-const char *luma_b200_temporal_blocking_status(luma_b200_t *h);
 /* on != 0: bracket each launch of the dominant kernel with CUDA events on its stream (read back by
  * luma_b200_stats); enabling resets the accumulators.  Off by default. */
 int  luma_b200_set_profiling(luma_b200_t *h, int32_t on);

@@ -48,8 +48,7 @@ class LumaStats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("ms_last_call", C.c_double), ("ms_per_step", C.c_double),
                 ("mlups_last_call", C.c_double), ("kernel_launches", C.c_int64),
                 ("halo_bytes_per_step", C.c_int64), ("cells", C.c_int64),
-                ("step_kernel_launches", C.c_int64), ("step_kernel_ms", C.c_double), ("step_kernel_cells", C.c_int64),
-                ("fused_steps", C.c_int64)]
+                ("step_kernel_launches", C.c_int64), ("step_kernel_ms", C.c_double), ("step_kernel_cells", C.c_int64)]
 
 
 class LumaHaloMsg(C.Structure):
@@ -111,13 +110,10 @@ def load(build_if_missing: bool = True):
     L.luma_b200_stats.argtypes = [H, C.POINTER(LumaStats)]
     L.luma_b200_sync.argtypes = [H]
     L.luma_b200_set_profiling.argtypes = [H, C.c_int32]
-    L.luma_b200_set_temporal_blocking.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
-    L.luma_b200_temporal_blocking_status.restype = C.c_char_p
-    L.luma_b200_temporal_blocking_status.argtypes = [H]
     L.luma_b200_halo_plan.argtypes = [C.POINTER(LumaCaseParams), C.POINTER(LumaHaloMsg), C.c_int32, _ip]
     L.luma_b200_selftest_div_const.argtypes = [C.c_int32, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     for nm in ("create", "slab", "comm_unique_id", "comm_init", "upload", "init_synthetic", "step", "download",
-               "download_lattyp", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan", "set_temporal_blocking"):
+               "download_lattyp", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
         getattr(L, "luma_b200_" + nm).restype = C.c_int
     if L.luma_b200_abi_version() != 1:
         raise ImportError("libluma_b200.so ABI version mismatch")

@@ -81,20 +81,6 @@ struct luma_b200
 	bool stepped = false;
 	LumaStats st;
 	std::string err;
-	// two-steps-per-sweep path (k_step2)
-	int tb_mode = 0;            // 0 off, 1 on when the case is eligible
-	int tb_rows = 0, tb_lag = 0, tb_ring = 0;   // 0 = automatic
-	bool tb_ready = false;      // schedule built for the current geometry
-	bool tb_eligible = false;
-	std::string tb_why;         // why the case is not eligible
-	Row2 *tb_rows_dev = nullptr;
-	int tb_nrowtasks = 0, tb_tiles_per_row = 0, tb_fluid_tiles = 0;
-	int *tb_bc_plane_start = nullptr;
-	unsigned *tb_counters = nullptr, *tb_ticket = nullptr;
-	double *tb_T = nullptr;
-	long long tb_tstride = 0;
-	unsigned tb_epoch = 0;
-	std::vector<int> bc_plane_start_host;
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
 	size_t prof_used = 0;
@@ -135,127 +121,6 @@ static void make_constants(LbmConst &C, int Q)
 	if (Q == 19) { C.w[0] = 1.0 / 18.0; C.w[1] = 1.0 / 36.0; C.w[2] = 1.0 / 3.0; }      // src/stdafx.cpp:140-143
 	else { C.w[0] = 1.0 / 9.0; C.w[1] = 1.0 / 36.0; C.w[2] = 4.0 / 9.0; }                // :147-148
 	for (int k = 0; k < 3; ++k) C.wden[k] = C.w[k] / C.den;
-}
-
-// ------------------------------------------------------------------------------------------------
-// two time steps per sweep: the host builds the list of row-tasks (kernels.cuh Row2) once per geometry
-// ------------------------------------------------------------------------------------------------
-static int env_int(const char *name, int dflt)
-{
-	const char *v = getenv(name);
-	return (v && *v) ? atoi(v) : dflt;
-}
-
-static int build_tb_schedule(luma_b200_t *h)
-{
-	const LumaCaseParams &p = h->p;
-	h->tb_ready = false;
-	if (!h->tb_mode) return LUMA_B200_OK;
-	if (h->ghost) { h->tb_why = "multi-rank slabs use the one-step path"; return LUMA_B200_OK; }
-	if (!h->tb_eligible) return LUMA_B200_OK;
-	const int P = h->P, M = p.M, K = p.K;
-	const int lag = h->tb_lag > 0 ? h->tb_lag : env_int("LUMA_B200_TB_LAG", 4);
-	const int ring = h->tb_ring > 0 ? h->tb_ring : env_int("LUMA_B200_TB_RING", lag + 3);
-	if (ring < lag + 2 || ring < 4 || P < lag + 3) { h->tb_why = "too few planes for the sweep pipeline"; return LUMA_B200_OK; }
-	int rows = h->tb_rows > 0 ? h->tb_rows : env_int("LUMA_B200_TB_ROWS", 0);
-	if (rows <= 0)
-	{
-		const long long target_sites = env_int("LUMA_B200_TB_SITES", 24576);   // sites per strip-plane
-		rows = (int)std::max<long long>(2, std::min<long long>(M, target_sites / std::max(1, K)));
-	}
-	rows = std::min(rows, M);
-	const int nstrips = (M + rows - 1) / rows;
-	rows = (M + nstrips - 1) / nstrips;
-	const long long slot_elems = (((long long)(rows + 2) * K) + 15) / 16 * 16;
-
-	std::vector<Row2> tasks;
-	std::vector<int> slot_owner((size_t)ring, -1);
-	std::vector<std::vector<int>> slot_readers((size_t)ring);
-	std::vector<int> cur_slot((size_t)P, -1), cur_row1((size_t)P, -1);
-	long long next_slot = 0;
-	bool ok = true;
-
-	auto emit_s1 = [&](int pl, int j0, int nr)
-	{
-		const int slot = (int)(next_slot++ % ring);
-		Row2 t; memset(&t, 0, sizeof(t));
-		t.step = 1; t.plane = pl; t.j_begin = (j0 - 1 + M) % M; t.nrows = nr + 2;
-		t.t_out = (long long)slot * slot_elems;
-		for (int rid : slot_readers[(size_t)slot])
-		{
-			if (t.ndep < 3) t.dep[t.ndep++] = rid; else ok = false;
-		}
-		slot_readers[(size_t)slot].clear();
-		if (slot_owner[(size_t)slot] >= 0 && cur_slot[(size_t)slot_owner[(size_t)slot]] == slot) cur_slot[(size_t)slot_owner[(size_t)slot]] = -1;
-		slot_owner[(size_t)slot] = pl;
-		cur_slot[(size_t)pl] = slot;
-		cur_row1[(size_t)pl] = (int)tasks.size();
-		tasks.push_back(t);
-	};
-	auto emit_s2 = [&](int pl, int j0, int nr)
-	{
-		Row2 t; memset(&t, 0, sizeof(t));
-		t.step = 2; t.plane = pl; t.j_begin = j0; t.nrows = nr;
-		const int src[3] = { (pl - 1 + P) % P, pl, (pl + 1) % P };
-		for (int x = 0; x < 3; ++x)
-		{
-			const int sl = cur_slot[(size_t)src[x]];
-			if (sl < 0) { ok = false; continue; }
-			t.t_in[x] = (long long)sl * slot_elems;
-			const int rid = cur_row1[(size_t)src[x]];
-			bool seen = false;
-			for (int d = 0; d < t.ndep; ++d) seen = seen || t.dep[d] == rid;
-			if (!seen) t.dep[t.ndep++] = rid;
-			slot_readers[(size_t)sl].push_back((int)tasks.size());
-		}
-		tasks.push_back(t);
-	};
-
-	for (int s = 0; s < nstrips; ++s)
-	{
-		const int j0 = s * rows, j1 = std::min(M, j0 + rows), nr = j1 - j0;
-		if (nr <= 0) break;
-		std::fill(cur_slot.begin(), cur_slot.end(), -1);      // T of the previous strip is not this strip's
-		int done2 = 0;                                         // step-2 planes 1..done2 emitted
-		for (int n = 0; n < P; ++n)
-		{
-			emit_s1(n, j0, nr);
-			const int q = n - lag;
-			if (q >= 1 && q <= P - 2) { emit_s2(q, j0, nr); done2 = q; }
-		}
-		for (int q = done2 + 1; q <= P - 2; ++q) emit_s2(q, j0, nr);
-		// periodic closure in x: planes 0 and 1 of the intermediate level are recomputed, then P-1 and 0 finish
-		emit_s1(0, j0, nr); emit_s2(P - 1, j0, nr);
-		emit_s1(1, j0, nr); emit_s2(0, j0, nr);
-	}
-	if (!ok) { h->tb_why = "internal: sweep schedule inconsistent"; return LUMA_B200_OK; }
-
-	int max_bc = 0;
-	for (int pl = 0; pl < P; ++pl) max_bc = std::max(max_bc, h->bc_plane_start_host[(size_t)pl + 1] - h->bc_plane_start_host[(size_t)pl]);
-	h->tb_fluid_tiles = (int)(((long long)(rows + 2) * K + 127) / 128);
-	h->tb_tiles_per_row = h->tb_fluid_tiles + (max_bc + 127) / 128;
-	h->tb_nrowtasks = (int)tasks.size();
-	h->tb_tstride = (long long)ring * slot_elems;
-	if ((long long)h->tb_nrowtasks * h->tb_tiles_per_row > 0x7fffffffLL) { h->tb_why = "sweep too long for one launch"; return LUMA_B200_OK; }
-
-	cudaFree(h->tb_rows_dev); cudaFree(h->tb_bc_plane_start); cudaFree(h->tb_counters); cudaFree(h->tb_ticket); cudaFree(h->tb_T);
-	h->tb_rows_dev = nullptr; h->tb_bc_plane_start = nullptr; h->tb_counters = nullptr; h->tb_ticket = nullptr; h->tb_T = nullptr;
-	cudaError_t e = cudaMalloc(&h->tb_rows_dev, tasks.size() * sizeof(Row2));
-	if (e == cudaSuccess) e = cudaMalloc(&h->tb_bc_plane_start, ((size_t)P + 1) * sizeof(int));
-	if (e == cudaSuccess) e = cudaMalloc(&h->tb_counters, tasks.size() * sizeof(unsigned));
-	if (e == cudaSuccess) e = cudaMalloc(&h->tb_ticket, sizeof(unsigned));
-	if (e == cudaSuccess) e = cudaMalloc(&h->tb_T, (size_t)h->tb_tstride * h->Q * sizeof(double));
-	if (e != cudaSuccess) { cudaGetLastError(); FAIL(LUMA_B200_ENOMEM, "temporal-blocking buffers"); }
-	CK(cudaMemcpyAsync(h->tb_rows_dev, tasks.data(), tasks.size() * sizeof(Row2), cudaMemcpyHostToDevice, h->s_main));
-	CK(cudaMemcpyAsync(h->tb_bc_plane_start, h->bc_plane_start_host.data(), ((size_t)P + 1) * sizeof(int), cudaMemcpyHostToDevice, h->s_main));
-	CK(cudaMemsetAsync(h->tb_counters, 0, tasks.size() * sizeof(unsigned), h->s_main));
-	CK(cudaMemsetAsync(h->tb_T, 0, (size_t)h->tb_tstride * h->Q * sizeof(double), h->s_main));
-	CK(cudaStreamSynchronize(h->s_main));
-	h->tb_epoch = 0;
-	h->tb_ready = true;
-	h->tb_why = "on: " + std::to_string(nstrips) + " strips of " + std::to_string(rows) + " rows, lag " + std::to_string(lag) +
-		", ring " + std::to_string(ring) + " slots (" + std::to_string((long long)h->tb_tstride * h->Q * 8 / (1 << 20)) + " MiB)";
-	return LUMA_B200_OK;
 }
 
 static cudaEvent_t prof_event(luma_b200_t *h)
@@ -342,7 +207,6 @@ static void free_all(luma_b200_t *h)
 {
 	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
 	cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->cw); cudaFree(h->bcdesc); cudaFree(h->types);
-	cudaFree(h->tb_rows_dev); cudaFree(h->tb_bc_plane_start); cudaFree(h->tb_counters); cudaFree(h->tb_ticket); cudaFree(h->tb_T);
 	cudaFree(h->rho); cudaFree(h->u); cudaFree(h->uin); cudaFree(h->bc_list); cudaFree(h->staging); cudaFree(h->momex_dev);
 	if (h->ev_edge) cudaEventDestroy(h->ev_edge);
 	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
@@ -382,7 +246,6 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	h->t = p->t;
 	memset(&h->st, 0, sizeof(h->st));
 	h->st.cells = (long long)p->x_count * h->MK;
-	h->tb_mode = env_int("LUMA_B200_TB", 0) ? 1 : 0;
 	make_constants(h->C, h->Q);
 	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 
@@ -538,11 +401,8 @@ static int finalize_geometry(luma_b200_t *h)
 
 	std::vector<long long> list;
 	const int pb = h->ghost, pe = h->P - h->ghost;
-	h->tb_eligible = true; h->tb_why.clear();
-	h->bc_plane_start_host.assign((size_t)h->P + 1, 0);
 	for (int pl = pb; pl < pe; ++pl)
 	{
-		h->bc_plane_start_host[(size_t)pl] = (int)list.size();
 		for (int j = 0; j < p.M; ++j)
 			for (int k = 0; k < p.K; ++k)
 			{
@@ -574,16 +434,9 @@ static int finalize_geometry(luma_b200_t *h)
 							FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from another boundary site (loop-order dependent in the reference)");
 					}
 				}
-				// the two-step sweep handles velocity FACES whose normal has no x component (no neighbour moments,
-				// no dependence on other planes of the same time level)
-				if (t != LUMA_E_VELOCITY || ec != 1 || ((d >> CW_N_SHIFT) & 3u) != 1u)
-				{ h->tb_eligible = false; h->tb_why = "boundary sites other than velocity faces with an in-plane normal"; }
 				list.push_back(id);
 			}
 	}
-	for (int pl = pe; pl <= h->P; ++pl) h->bc_plane_start_host[(size_t)pl] = (int)list.size();
-	for (int pl = 0; pl < pb; ++pl) h->bc_plane_start_host[(size_t)pl] = 0;
-	h->tb_ready = false;
 	cudaFree(h->bc_list); h->bc_list = nullptr;
 	h->n_bc = (int)list.size();
 	if (h->n_bc)
@@ -679,7 +532,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	}
 	h->t = p.t; h->omega = p.omega;
 	h->have_state = true; h->stepped = false;
-	return build_tb_schedule(h);
+	return LUMA_B200_OK;
 }
 
 int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
@@ -720,23 +573,6 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	h->t = p.t; h->omega = p.omega;
 	h->have_state = true; h->stepped = false;
 	return LUMA_B200_OK;
-}
-
-int luma_b200_set_temporal_blocking(luma_b200_t *h, int32_t mode, int32_t rows_per_strip, int32_t lag, int32_t ring_slots)
-{
-	if (!h) return LUMA_B200_EINVAL;
-	if (mode < 0 || mode > 1 || rows_per_strip < 0 || lag < 0 || ring_slots < 0) FAIL(LUMA_B200_EINVAL, "set_temporal_blocking");
-	h->tb_mode = mode; h->tb_rows = rows_per_strip; h->tb_lag = lag; h->tb_ring = ring_slots;
-	h->tb_ready = false;
-	if (h->have_state) return build_tb_schedule(h);
-	return LUMA_B200_OK;
-}
-
-const char *luma_b200_temporal_blocking_status(luma_b200_t *h)
-{
-	if (!h) return "null handle";
-	if (!h->tb_mode) return "off";
-	return h->tb_why.c_str();
 }
 
 int luma_b200_set_profiling(luma_b200_t *h, int32_t on)
@@ -800,40 +636,6 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	int s = 0;
 	while (s < nsteps)
 	{
-		// two steps per sweep while at least one more step follows (the last step of a call is always a
-		// plain one: it stores rho,u and leaves the pre-stream populations of the LAST step in the other
-		// lattice, which luma_b200_forces needs)
-		if (h->tb_ready && nsteps - s >= 3)
-		{
-			Step2Args b;
-			b.s1 = a; b.s2 = a;
-			step_scalars(b.s1, h->t);
-			step_scalars(b.s2, h->t + 1);
-			b.s1.fin = h->f[h->cur]; b.s1.fout = nullptr; b.s1.write_macro = 0;
-			b.s2.fin = nullptr; b.s2.fout = h->f[h->cur ^ 1]; b.s2.write_macro = 0;
-			b.T = h->tb_T; b.tstride = h->tb_tstride;
-			b.rows = h->tb_rows_dev;
-			b.tiles_per_row = h->tb_tiles_per_row; b.fluid_tiles = h->tb_fluid_tiles;
-			b.bc_plane_start = h->tb_bc_plane_start;
-			b.counters = h->tb_counters;
-			b.target = (unsigned)h->tb_tiles_per_row * (++h->tb_epoch);
-			b.ticket = h->tb_ticket;
-			CK(cudaMemsetAsync(h->tb_ticket, 0, sizeof(unsigned), h->s_main));
-			if (h->profiling) cudaEventRecord(prof_event(h), h->s_main);
-			if (h->Q == 19) launch_step2<D3Q19>(b, smag, force, h->tb_nrowtasks, h->s_main, &h->st.kernel_launches);
-			else launch_step2<D2Q9>(b, smag, force, h->tb_nrowtasks, h->s_main, &h->st.kernel_launches);
-			if (h->profiling)
-			{
-				cudaEventRecord(prof_event(h), h->s_main);
-				h->st.step_kernel_launches++;
-				h->st.step_kernel_cells += 2LL * h->P * h->MK;
-			}
-			h->st.fused_steps += 2;
-			h->cur ^= 1;
-			h->t += 2;
-			s += 2;
-			continue;
-		}
 		step_scalars(a, h->t);
 		a.fin = h->f[h->cur]; a.fout = h->f[h->cur ^ 1];
 		a.write_macro = (s == nsteps - 1) ? 1 : 0;

@@ -329,219 +329,6 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 	store_populations<L>(a, id, f);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Two time steps per sweep.  DRAM sees lattice A once (read) and lattice B once (written) per TWO
-// lattice updates; the intermediate time level lives in the ring T, which is small enough to stay
-// in the 126 MB L2 (slots are recycled, so their dirty lines are overwritten before they are
-// evicted).  Arithmetic per site is exactly that of k_step / k_bc, so results stay bit-identical.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long l2_policy_evict_last()
-{
-	unsigned long long pol;
-	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_first()
-{
-	unsigned long long pol;
-	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-	return pol;
-}
-// ring accesses bypass L1 (slots are rewritten by other SMs during the kernel) and ask L2 to keep the line
-__device__ __forceinline__ double ring_load(const double *p, const unsigned long long pol)
-{
-	double v;
-	asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
-	return v;
-}
-__device__ __forceinline__ void ring_store(double *p, const double v, const unsigned long long pol)
-{
-	asm volatile("st.global.cg.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
-{
-	unsigned v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
-// pull of one site from the ring: plane p - c_x selects the slot, rows never wrap (the slot carries
-// one halo row each side), z wraps inside the row
-template <class L>
-__device__ __forceinline__ void pull_from_ring(const Step2Args &a, const long long (&t_in)[3], const int K, const long long lsT,
-	const int k, const uint32_t w, const unsigned long long pol, double (&f)[L::Q])
-{
-	const bool zedge = (L::D == 3) && (k == 0 || k == K - 1);
-	const double *base = a.T + lsT;
-	if ((w & CW_LINKS) == 0 && !zedge)
-	{
-#pragma unroll
-		for (int v = 0; v < L::Q; ++v)
-		{
-			const int cx = L::c(v, 0), cy = L::c(v, 1), cz = L::c(v, 2);
-			const long long off = (long long)v * a.tstride + t_in[1 - cx] - (long long)cy * K - cz;
-			f[v] = ring_load(base + off, pol);
-		}
-		return;
-	}
-	const long long zm = (L::D == 3 && k == 0) ? (long long)(K - 1) : -1;
-	const long long zp = (L::D == 3 && k == K - 1) ? -(long long)(K - 1) : 1;
-#pragma unroll
-	for (int v = 0; v < L::Q; ++v)
-	{
-		const int cx = L::c(v, 0), cy = L::c(v, 1), cz = L::c(v, 2);
-		long long off = (long long)v * a.tstride + t_in[1 - cx] - (long long)cy * K;
-		if (cz == 1) off += zm; else if (cz == -1) off += zp;
-		if (v < L::Q - 1)
-		{
-			if ((w >> v) & 1u) off = (long long)opposite<L>(v) * a.tstride + t_in[1];
-		}
-		f[v] = ring_load(base + off, pol);
-	}
-}
-
-// fluid sites of one row-task (the hot path)
-template <class L, bool SMAG, bool FORCE, int STEP>
-__device__ __forceinline__ void fused_fluid_tile(const Step2Args &a, const StepArgs &s, const Row2 *rw, const int tile)
-{
-	const int p = __ldg(&rw->plane), j_begin = __ldg(&rw->j_begin), nrows = __ldg(&rw->nrows);
-	const int K = s.K;
-	const unsigned ls = (unsigned)tile * STEP_THREADS + threadIdx.x;
-	const int lj = (int)(ls / (unsigned)K);
-	const int k = (int)(ls - (unsigned)lj * (unsigned)K);
-	if (lj >= nrows) return;
-	int j = j_begin + lj;
-	if (j >= s.M) j -= s.M;
-	const unsigned r = (unsigned)j * (unsigned)K + (unsigned)k;
-	const long long id = (long long)p * s.MK + r;
-	const uint32_t w = __ldg(s.cw + id);
-	if (cw_class(w) != CLS_FLUID) return;
-	const unsigned long long pol = l2_policy_evict_last();
-
-	double f[L::Q], feq[L::Q], u[3], rho;
-	if (STEP == 1) pull_populations<L>(s, p, r, id, w, f);
-	else
-	{
-		const long long t_in[3] = { __ldg(&rw->t_in[0]), __ldg(&rw->t_in[1]), __ldg(&rw->t_in[2]) };
-		pull_from_ring<L>(a, t_in, K, (long long)(lj + 1) * K + k, k, w, pol, f);
-	}
-	macroscopic<L, FORCE>(f, s.hF, rho, u);
-	equilibrium_all<L>(rho, u, s.C, feq);
-	collide<L, SMAG, FORCE>(s, u, feq, f);
-	if (STEP == 1)
-	{
-		double *tb = a.T + __ldg(&rw->t_out) + (long long)lj * K + k;
-#pragma unroll
-		for (int v = 0; v < L::Q; ++v) ring_store(tb + (long long)v * a.tstride, f[v], pol);
-	}
-	else
-	{
-		store_populations<L>(s, id, f);
-		if (s.write_macro)
-		{
-			s.rho[id] = rho;
-#pragma unroll
-			for (int d = 0; d < L::D; ++d) s.u[(long long)d * s.stride + id] = u[d];
-		}
-	}
-}
-
-// velocity-face sites of one row-task (rare; kept out of line so that its registers do not weigh on the hot path)
-template <class L, bool SMAG, bool FORCE, int STEP>
-__device__ __noinline__ void fused_boundary_tile(const Step2Args &a, const StepArgs &s, const Row2 *rw, const int tile)
-{
-	const int p = rw->plane, j_begin = rw->j_begin, nrows = rw->nrows;
-	const int K = s.K;
-	const int i = (tile - a.fluid_tiles) * STEP_THREADS + (int)threadIdx.x;
-	const int b0 = a.bc_plane_start[p], b1 = a.bc_plane_start[p + 1];
-	if (b0 + i >= b1) return;
-	const long long id = s.bc_list[b0 + i];
-	const unsigned r = (unsigned)(id - (long long)p * s.MK);
-	const int j = (int)(r / (unsigned)K);
-	const int k = (int)(r - (unsigned)j * (unsigned)K);
-	int lj = j - j_begin;
-	if (lj < 0) lj += s.M;
-	if (lj >= nrows) return;
-	const uint32_t w = s.cw[id];
-	const unsigned long long pol = l2_policy_evict_last();
-
-	double f[L::Q], u[3], rho;
-	if (STEP == 1) pull_populations<L>(s, p, r, id, w, f);
-	else
-	{
-		const long long t_in[3] = { rw->t_in[0], rw->t_in[1], rw->t_in[2] };
-		pull_from_ring<L>(a, t_in, K, (long long)(lj + 1) * K + k, k, w, pol, f);
-	}
-	// only velocity faces reach this kernel (checked on the host): no neighbour moments needed
-	const double z3[3] = { 0.0, 0.0, 0.0 };
-	bc_regularise<L, SMAG, FORCE>(s, w, j, f, 0.0, z3, 0.0, z3, rho, u);
-	if (STEP == 1)
-	{
-		// a strip that spans all M rows carries its first and last row twice (as halo rows): store both copies
-		for (int l2 = lj; l2 < nrows; l2 += s.M)
-		{
-			double *tb = a.T + rw->t_out + (long long)l2 * K + k;
-#pragma unroll
-			for (int v = 0; v < L::Q; ++v) ring_store(tb + (long long)v * a.tstride, f[v], pol);
-		}
-	}
-	else store_populations<L>(s, id, f);
-	s.rho[id] = rho;
-#pragma unroll
-	for (int d = 0; d < L::D; ++d) s.u[(long long)d * s.stride + id] = u[d];
-}
-
-template <class L, bool SMAG, bool FORCE>
-__global__ void __launch_bounds__(STEP_THREADS, SMAG ? LUMA_MIN_BLOCKS_SMAG : LUMA_MIN_BLOCKS) k_step2(const __grid_constant__ Step2Args a)
-{
-	__shared__ unsigned s_ticket;
-	if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
-	__syncthreads();
-	const unsigned ticket = s_ticket;
-	const int rowi = (int)(ticket / (unsigned)a.tiles_per_row);
-	const int tile = (int)(ticket - (unsigned)rowi * (unsigned)a.tiles_per_row);
-	const Row2 *rw = a.rows + rowi;
-
-	// wait for the row-tasks this one depends on (they were handed out earlier, so they are running or done)
-	const int ndep = __ldg(&rw->ndep);
-	if ((int)threadIdx.x < ndep)
-	{
-		const unsigned *c = a.counters + __ldg(&rw->dep[threadIdx.x]);
-		while (ld_acquire_u32(c) < a.target) __nanosleep(100);
-	}
-	__syncthreads();
-
-	const bool first = __ldg(&rw->step) == 1;
-	if (tile < a.fluid_tiles)
-	{
-		if (first) fused_fluid_tile<L, SMAG, FORCE, 1>(a, a.s1, rw, tile);
-		else fused_fluid_tile<L, SMAG, FORCE, 2>(a, a.s2, rw, tile);
-	}
-	else
-	{
-		if (first) fused_boundary_tile<L, SMAG, FORCE, 1>(a, a.s1, rw, tile);
-		else fused_boundary_tile<L, SMAG, FORCE, 2>(a, a.s2, rw, tile);
-	}
-
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		__threadfence();
-		atomicAdd(a.counters + rowi, 1u);
-	}
-}
-
-template <class L> void launch_step2(const Step2Args &a, bool smag, bool force, int nrowtasks, cudaStream_t s, int64_t *launches)
-{
-	if (nrowtasks <= 0) return;
-	const unsigned grid = (unsigned)nrowtasks * (unsigned)a.tiles_per_row;
-	if (smag && force) k_step2<L, true, true><<<grid, STEP_THREADS, 0, s>>>(a);
-	else if (smag) k_step2<L, true, false><<<grid, STEP_THREADS, 0, s>>>(a);
-	else if (force) k_step2<L, false, true><<<grid, STEP_THREADS, 0, s>>>(a);
-	else k_step2<L, false, false><<<grid, STEP_THREADS, 0, s>>>(a);
-	if (launches) ++*launches;
-}
-
 template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches)
 {
 	if (nplanes <= 0) return;
@@ -863,7 +650,6 @@ void launch_selftest_div(const LbmConst &C, unsigned long long seed, long long n
 #define LUMA_INST(L) \
 	template void launch_step<L>(const StepArgs &, bool, bool, int, cudaStream_t, int64_t *); \
 	template void launch_bc<L>(const StepArgs &, bool, bool, cudaStream_t, int64_t *); \
-	template void launch_step2<L>(const Step2Args &, bool, bool, int, cudaStream_t, int64_t *); \
 	template void launch_cell_words<L>(const GeomArgs &, cudaStream_t); \
 	template void launch_synthetic<L>(const SynthArgs &, cudaStream_t); \
 	template void launch_aos_to_soa<L>(const double *, double *, long long, long long, long long, cudaStream_t); \

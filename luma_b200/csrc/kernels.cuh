@@ -35,37 +35,6 @@ struct StepArgs
 	double rho_out;
 };
 
-// ---- two time steps per sweep (temporal blocking through L2, kernels.cu k_step2) ----
-// The sweep is a list of row-tasks built on the host.  A row-task is one time step applied to a strip of
-// rows [j_begin, j_begin+nrows) (wrapping modulo M) of one x-plane: step 1 reads lattice A and writes
-// the strip into a slot of the small ring T that lives in L2; step 2 reads three T slots (planes p-1,
-// p, p+1) and writes lattice B.  Row-tasks are handed to CTAs in list order; `dep` names earlier
-// row-tasks that must be complete (RAW on T for step 2, WAR on the recycled T slot for step 1).
-struct Row2
-{
-	int step;                 // 1: A -> T,  2: T -> B
-	int plane;                // local plane p
-	int j_begin, nrows;       // rows of sites of this task
-	int ndep;
-	int dep[3];
-	long long t_out;          // step 1: element offset in T of (row j_begin, k = 0)
-	long long t_in[3];        // step 2: element offsets in T of (row j_begin-1, k = 0) for planes p-1, p, p+1
-};
-
-struct Step2Args
-{
-	StepArgs s1, s2;          // per-step scalars; s1.fin = lattice A, s2.fout = lattice B
-	double *T;                // ring [Q][tstride]
-	long long tstride;
-	const Row2 *rows;
-	int tiles_per_row;        // CTAs per row-task (fluid tiles first, then boundary tiles)
-	int fluid_tiles;
-	const int *bc_plane_start;// [P+1] offsets into bc_list (sorted by plane)
-	unsigned *counters;       // completed CTAs per row-task, monotonic over launches
-	unsigned target;          // tiles_per_row * (number of sweeps launched so far, this one included)
-	unsigned *ticket;         // zeroed before every launch
-};
-
 struct GeomArgs
 {
 	const uint8_t *types;     // eType per cell [cells]
@@ -100,7 +69,6 @@ struct SynthArgs
 
 template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches);
-template <class L> void launch_step2(const Step2Args &a, bool smag, bool force, int nrowtasks, cudaStream_t s, int64_t *launches);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);
 template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first_cell, long long ncells, cudaStream_t s);

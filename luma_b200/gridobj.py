@@ -177,14 +177,6 @@ class GridObj:
         capi.check(self._L.luma_b200_stats(self._h, C.byref(s)), self._h)
         return {k: getattr(s, k) for k, _ in s._fields_}
 
-    def set_temporal_blocking(self, on: bool = True, rows_per_strip: int = 0, lag: int = 0, ring_slots: int = 0):
-        """Two time steps per sweep through the L2 (bit-identical results); see include/luma_b200.h."""
-        capi.check(self._L.luma_b200_set_temporal_blocking(self._h, int(on), rows_per_strip, lag, ring_slots), self._h)
-        return self
-
-    def temporal_blocking_status(self) -> str:
-        return self._L.luma_b200_temporal_blocking_status(self._h).decode()
-
     def set_profiling(self, on: bool = True):
         capi.check(self._L.luma_b200_set_profiling(self._h, int(on)), self._h)
 

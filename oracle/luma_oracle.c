@@ -14,7 +14,7 @@
 #include <string.h>
 
 /* inc/Enumerations.h:84-96 */
-enum { eSolid = 0, eFluid = 1, eRefined = 2, eVelocity = 6, ePressure = 7 };
+enum { eSolid = 0, eFluid = 1, eRefined = 2, eVelocity = 6, ePressure = 7, eSlip = 8, eExtrapolateRight = 9 };
 /* inc/stdafx.h:112-114 */
 #define ORC_SQRT2 1.4142135623730950488016887242097
 #define ORC_PI 3.14159265358979323846
@@ -38,7 +38,9 @@ struct OracleGrid {
 	int t;
 	double *xpos, *ypos, *zpos;
 	double *uin[3];
+	int reflect[3][19];        /* GridUtils::dir_reflect, src/GridUtils.cpp:46-51,:60-64 */
 	double *f, *fnew, *rho, *u, *force_xyz, *force_i;
+	double *rho_timeav, *ui_timeav, *uiuj_timeav;   /* inc/GridObj.h:93-95, src/GridObj_init_grids.cpp:304-306 */
 	int32_t *lattyp, *wall;
 	double momex[3];
 	int err;
@@ -132,10 +134,27 @@ static double feq_at(const OracleGrid *g, size_t id, int v)
 	return g->rho[id] * g->w[v] * (1.0 + (A / SQ(cs)) + (B / (2.0 * SQ(cs) * SQ(cs))));
 }
 
-/* GridObj::_LBM_stream_opt, src/GridObj_ops_lbm_optimised.cpp:206-297 (no BFL, slip, refinement) */
+/* GridObj::_LBM_applySpecReflect_opt, src/GridObj_ops_lbm_optimised.cpp:527-581: the first wall,
+ * in the order left, right, bottom, top, front, back, whose inward normal component equals the
+ * link's component reflects the link in that direction. */
+static int spec_reflect(OracleGrid *g, int i, int j, int k, size_t id, int v)
+{
+	int32_t wd[5];
+	if (!within_domain_wall(g, g->xpos[i], g->ypos[j], g->zpos[k], wd)) { g->err = 4; return 0; }
+	const int32_t *n = &wd[2];
+	for (int d = 0; d < 3; ++d)
+	{
+		if (n[d] == 1 && g->c[v][d] == 1) { g->fnew[v + id * g->Q] = g->f[g->reflect[d][v] + id * g->Q]; return 1; }
+		if (n[d] == -1 && g->c[v][d] == -1) { g->fnew[v + id * g->Q] = g->f[g->reflect[d][v] + id * g->Q]; return 1; }
+	}
+	return 0;
+}
+
+/* GridObj::_LBM_stream_opt, src/GridObj_ops_lbm_optimised.cpp:206-297 (no BFL, refinement) */
 static void stream_site(OracleGrid *g, int i, int j, int k, size_t id)
 {
 	const int Q = g->Q;
+	const int32_t type = g->lattyp[id];
 	for (int v = 0; v < Q; ++v)
 	{
 		int sx = (i - g->c[v][0] + g->N) % g->N;
@@ -143,10 +162,22 @@ static void stream_site(OracleGrid *g, int i, int j, int k, size_t id)
 		int sz = (k - g->c[v][2] + g->K) % g->K;
 		size_t src = site_id(g, sx, sy, sz);
 		int32_t st = g->lattyp[src];
+		if (type == eSlip)
+		{
+			/* slip :229-233 */
+			if (spec_reflect(g, i, j, k, id, v)) continue;
+			if (g->err) return;
+		}
 		if (st == eSolid)
 		{
 			/* halfway bounce-back :238-243 */
 			g->fnew[v + id * Q] = g->f[g->opp[v] + id * Q];
+		}
+		else if (st == eExtrapolateRight)
+		{
+			/* the value two sites to the left of the source :246-251 */
+			if (sx < 2) { g->err = 3; return; }
+			g->fnew[v + id * Q] = g->f[v + (src - 2 * ((size_t)g->K * g->M)) * Q];
 		}
 		else if (!g->cs_.regularised && st == eVelocity)
 		{
@@ -167,10 +198,33 @@ static void stream_site(OracleGrid *g, int i, int j, int k, size_t id)
 	}
 }
 
-/* GridObj::_LBM_macro_opt, src/GridObj_ops_lbm_optimised.cpp:800-847 (no time averages) */
-static void macro_site(OracleGrid *g, size_t id, int32_t type)
+/* time-averaged statistics, src/GridObj_ops_lbm_optimised.cpp:895-917 */
+static void time_average_site(OracleGrid *g, size_t id)
 {
-	if (type != eFluid) return;   /* eBFL/eSlip/eTransitionToFiner never occur here */
+	const int D = g->D, P = 3 * D - 3, t = g->t;
+	double ta_temp = g->rho_timeav[id] * (double)t;
+	ta_temp += g->rho[id];
+	g->rho_timeav[id] = ta_temp / (double)(t + 1);
+	int pq_combo = 0;
+	for (int p = 0; p < D; p++)
+	{
+		ta_temp = g->ui_timeav[p + id * D] * (double)t;
+		ta_temp += g->u[p + id * D];
+		g->ui_timeav[p + id * D] = ta_temp / (double)(t + 1);
+		for (int q = p; q < D; q++)
+		{
+			ta_temp = g->uiuj_timeav[pq_combo + id * P] * (double)t;
+			ta_temp += (g->u[p + id * D] * g->u[q + id * D]);
+			g->uiuj_timeav[pq_combo + id * P] = ta_temp / (double)(t + 1);
+			pq_combo++;
+		}
+	}
+}
+
+/* the moment sums of GridObj::_LBM_macro_opt, src/GridObj_ops_lbm_optimised.cpp:800-847 */
+static void macro_moments(OracleGrid *g, size_t id, int32_t type)
+{
+	if (type != eFluid && type != eSlip) return;   /* eBFL/eTransitionToFiner never occur here */
 	const int Q = g->Q, D = g->D;
 	double r = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
 	for (int v = 0; v < Q; ++v)
@@ -191,6 +245,13 @@ static void macro_site(OracleGrid *g, size_t id, int32_t type)
 	g->u[1 + id * D] = my / r;
 	if (D == 3) g->u[2 + id * D] = mz / r;
 	g->rho[id] = r;
+}
+
+/* GridObj::_LBM_macro_opt, src/GridObj_ops_lbm_optimised.cpp:800-918 */
+static void macro_site(OracleGrid *g, size_t id, int32_t type)
+{
+	macro_moments(g, id, type);
+	if (g->cs_.time_averaged) time_average_site(g, id);
 }
 
 /* GridUtils::isOffGrid, src/GridUtils.cpp:1533-1546 */
@@ -415,6 +476,7 @@ static void multi_opt(OracleGrid *g)
 				if (c->ld_out && type == eSolid) momex_site(g, i, j, k);
 				if (type == eRefined || type == eSolid || (!c->regularised && type == eVelocity)) continue;
 				stream_site(g, i, j, k, id);
+				if (g->err) return;
 				if (c->regularised && (type == eVelocity || type == ePressure))
 					regularised_site(g, i, j, k, id, type);
 				macro_site(g, id, type);
@@ -445,6 +507,15 @@ OracleGrid *luma_oracle_create(const OracleCase *c)
 		for (int d = 0; d < 3; ++d) g->c[v][d] = (D == 3) ? C19[v][d] : C9[v][d];
 	for (int v = 0; v < Q - 1; ++v) g->opp[v] = v ^ 1;
 	g->opp[Q - 1] = Q - 1;
+	/* dir_reflect[plane][v]: the direction with component `plane` negated */
+	for (int d = 0; d < 3; ++d)
+		for (int v = 0; v < Q; ++v)
+			for (int r = 0; r < Q; ++r)
+			{
+				int same = 1;
+				for (int e = 0; e < 3; ++e) same = same && (g->c[r][e] == ((e == d) ? -g->c[v][e] : g->c[v][e]));
+				if (same) g->reflect[d][v] = r;
+			}
 	if (D == 3)
 	{
 		for (int v = 0; v < 6; ++v) g->w[v] = 1.0 / 18.0;
@@ -484,8 +555,11 @@ OracleGrid *luma_oracle_create(const OracleCase *c)
 	g->u = (double *)malloc(ns * D * sizeof(double));
 	g->force_xyz = (double *)calloc(ns * D, sizeof(double));
 	g->force_i = (double *)calloc(ns * Q, sizeof(double));
+	g->rho_timeav = (double *)calloc(ns, sizeof(double));
+	g->ui_timeav = (double *)calloc(ns * D, sizeof(double));
+	g->uiuj_timeav = (double *)calloc(ns * (3 * D - 3), sizeof(double));
 	for (int d = 0; d < 3; ++d) g->uin[d] = (double *)calloc((size_t)g->M, sizeof(double));
-	if (!g->lattyp || !g->wall || !g->f || !g->fnew || !g->rho || !g->u || !g->force_xyz || !g->force_i)
+	if (!g->rho_timeav || !g->ui_timeav || !g->uiuj_timeav || !g->lattyp || !g->wall || !g->f || !g->fnew || !g->rho || !g->u || !g->force_xyz || !g->force_i)
 	{ luma_oracle_destroy(g); return NULL; }
 
 	/* LBM_initBoundLab :983-1097 -- order Left, Right, Front, Back, Bottom, Top */
@@ -581,6 +655,7 @@ void luma_oracle_destroy(OracleGrid *g)
 	free(g->xpos); free(g->ypos); free(g->zpos);
 	for (int d = 0; d < 3; ++d) free(g->uin[d]);
 	free(g->f); free(g->fnew); free(g->rho); free(g->u); free(g->force_xyz); free(g->force_i);
+	free(g->rho_timeav); free(g->ui_timeav); free(g->uiuj_timeav);
 	free(g->lattyp); free(g->wall);
 	free(g);
 }
@@ -589,6 +664,9 @@ double  *luma_oracle_f(OracleGrid *g) { return g->f; }
 double  *luma_oracle_fnew(OracleGrid *g) { return g->fnew; }
 double  *luma_oracle_rho(OracleGrid *g) { return g->rho; }
 double  *luma_oracle_u(OracleGrid *g) { return g->u; }
+double  *luma_oracle_rho_timeav(OracleGrid *g) { return g->rho_timeav; }
+double  *luma_oracle_ui_timeav(OracleGrid *g) { return g->ui_timeav; }
+double  *luma_oracle_uiuj_timeav(OracleGrid *g) { return g->uiuj_timeav; }
 int32_t *luma_oracle_lattyp(OracleGrid *g) { return g->lattyp; }
 int32_t *luma_oracle_wall(OracleGrid *g) { return g->wall; }
 double  *luma_oracle_uin(OracleGrid *g, int d) { return g->uin[d]; }

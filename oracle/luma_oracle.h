@@ -46,6 +46,7 @@ typedef struct OracleCase {
 	int32_t ld_out;             /* L_LD_OUT */
 	int32_t has_box;            /* bounce-back body given as an index box */
 	int32_t box[6];             /* i0,i1,j0,j1,k0,k1 (half-open) */
+	int32_t time_averaged;      /* L_COMPUTE_TIME_AVERAGED_QUANTITIES */
 } OracleCase;
 
 typedef struct OracleGrid OracleGrid;
@@ -56,7 +57,7 @@ void        luma_oracle_destroy(OracleGrid *g);
 
 /* nsteps calls of LBM_multi_opt.  Returns 0, or the code of the first fatal condition the
  * reference would L_ERROR on (1: BC site not within a wall, 2: pressure BC on edge/corner,
- * 3: extrapolation off grid). */
+ * 3: extrapolation off grid, 4: slip site outside a wall region). */
 int luma_oracle_step(OracleGrid *g, int nsteps);
 
 /* Views of the state, in the reference's AoS layout (inc/IVector.h:94-134). */
@@ -64,6 +65,9 @@ double  *luma_oracle_f(OracleGrid *g);        /* [N*M*K*Q]  f[v + Q*(k + K*(j + 
 double  *luma_oracle_fnew(OracleGrid *g);
 double  *luma_oracle_rho(OracleGrid *g);      /* [N*M*K] */
 double  *luma_oracle_u(OracleGrid *g);        /* [N*M*K*dims] */
+double  *luma_oracle_rho_timeav(OracleGrid *g);  /* [N*M*K]              time-averaged statistics,  */
+double  *luma_oracle_ui_timeav(OracleGrid *g);   /* [N*M*K*dims]         inc/GridObj.h:98-100       */
+double  *luma_oracle_uiuj_timeav(OracleGrid *g); /* [N*M*K*(3*dims-3)]                              */
 int32_t *luma_oracle_lattyp(OracleGrid *g);   /* [N*M*K] eType */
 int32_t *luma_oracle_wall(OracleGrid *g);     /* [N*M*K*5] {edgeCount, normalDirection, nx, ny, nz} */
 double  *luma_oracle_uin(OracleGrid *g, int d); /* ux_in/uy_in/uz_in [M] */

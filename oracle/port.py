@@ -38,6 +38,7 @@ class OracleCase(C.Structure):
         ("reynolds_ramp_on", C.c_int32), ("reynolds_ramp", C.c_double),
         ("parabolic_inlet", C.c_int32), ("pressure_delta", C.c_double),
         ("ld_out", C.c_int32), ("has_box", C.c_int32), ("box", C.c_int32 * 6),
+        ("time_averaged", C.c_int32),
     ]
 
 
@@ -71,6 +72,7 @@ def case_struct(case: Case, struct_type=OracleCase):
     if case.box is not None:
         for a in range(6):
             s.box[a] = case.box[a]
+    s.time_averaged = int(case.time_averaged)
     return s
 
 
@@ -94,7 +96,7 @@ def lib():
         L.luma_oracle_destroy.argtypes = [C.c_void_p]
         L.luma_oracle_step.restype = C.c_int
         L.luma_oracle_step.argtypes = [C.c_void_p, C.c_int]
-        for nm in ("f", "fnew", "rho", "u"):
+        for nm in ("f", "fnew", "rho", "u", "rho_timeav", "ui_timeav", "uiuj_timeav"):
             fn = getattr(L, "luma_oracle_" + nm)
             fn.restype = C.POINTER(C.c_double)
             fn.argtypes = [C.c_void_p]
@@ -165,6 +167,19 @@ class PortGrid:
     @property
     def u(self):
         return self._arr(self._L.luma_oracle_u, self.nsites * self.D, np.float64)
+
+    # time-averaged statistics (zeros unless the case sets time_averaged)
+    @property
+    def rho_timeav(self):
+        return self._arr(self._L.luma_oracle_rho_timeav, self.nsites, np.float64)
+
+    @property
+    def ui_timeav(self):
+        return self._arr(self._L.luma_oracle_ui_timeav, self.nsites * self.D, np.float64)
+
+    @property
+    def uiuj_timeav(self):
+        return self._arr(self._L.luma_oracle_uiuj_timeav, self.nsites * (3 * self.D - 3), np.float64)
 
     @property
     def lattyp(self):
@@ -249,6 +264,10 @@ def run_ref_dump(name: str, steps, outdir=None):
         d = {}
         for arr, dt in (("f", np.float64), ("rho", np.float64), ("u", np.float64)):
             d[arr] = np.fromfile(os.path.join(outdir, "%s.%s.f64" % (tag, arr)), dtype=dt)
+        for arr in ("rho_timeav", "ui_timeav", "uiuj_timeav"):
+            path = os.path.join(outdir, "%s.%s.f64" % (tag, arr))
+            if os.path.exists(path):
+                d[arr] = np.fromfile(path, dtype=np.float64)
         d["scalars"] = _read_kv(os.path.join(outdir, tag + ".scalars.txt"))
         if tag == "init":
             d["lattyp"] = np.fromfile(os.path.join(outdir, "init.lattyp.i32"), dtype=np.int32)

@@ -110,6 +110,12 @@ void GridObj::io_lite(double tval, std::string Tag)
 	write_raw(Tag + ".f.f64", &f[0], f.size() * sizeof(double));
 	write_raw(Tag + ".rho.f64", &rho[0], rho.size() * sizeof(double));
 	write_raw(Tag + ".u.f64", &u[0], u.size() * sizeof(double));
+#ifdef L_COMPUTE_TIME_AVERAGED_QUANTITIES
+	/* time-averaged statistics of _LBM_macro_opt (optimised.cpp:895-917) */
+	write_raw(Tag + ".rho_timeav.f64", &rho_timeav[0], rho_timeav.size() * sizeof(double));
+	write_raw(Tag + ".ui_timeav.f64", &ui_timeav[0], ui_timeav.size() * sizeof(double));
+	write_raw(Tag + ".uiuj_timeav.f64", &uiuj_timeav[0], uiuj_timeav.size() * sizeof(double));
+#endif
 	FILE *fh = fopen((Tag + ".scalars.txt").c_str(), "w");
 	ObjectManager *om = ObjectManager::getInstance();
 	fprintf(fh, "t=%d\nomega=%.17g\nFx=%.17g\nFy=%.17g\nFz=%.17g\n", t, omega,
