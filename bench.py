@@ -34,6 +34,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout at
+# NCCL_DEBUG=VERSION) would be a second one
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "MLUPS (D3Q19 fp64)"
 UNIT = "MLUPS"
