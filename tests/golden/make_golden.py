@@ -56,6 +56,9 @@ def make(name):
     for tag, d in res.items():
         g["snapshots"][tag] = {"f": digest(d["f"]), "rho": digest(d["rho"]), "u": digest(d["u"]),
                                "scalars": d["scalars"], "probes": probes(case, d)}
+        for nm in ("rho_timeav", "ui_timeav", "uiuj_timeav"):      # L_COMPUTE_TIME_AVERAGED_QUANTITIES cases
+            if nm in d:
+                g["snapshots"][tag][nm] = digest(d[nm])
     with open(os.path.join(HERE, name + ".json"), "w") as fh:
         json.dump(g, fh, indent=1, sort_keys=True)
         fh.write("\n")

@@ -56,6 +56,9 @@ def test_port_matches_golden_digests(name):
         assert snap["f"] == _digest(g.f), (name, tag, "f")
         assert snap["rho"] == _digest(g.rho), (name, tag, "rho")
         assert snap["u"] == _digest(g.u), (name, tag, "u")
+        if case.time_averaged:
+            for nm in ("rho_timeav", "ui_timeav", "uiuj_timeav"):
+                assert snap[nm] == _digest(getattr(g, nm)), (name, tag, nm)
         if tag != "init":
             assert float(snap["scalars"]["omega"]) == g.omega
             if case.ld_out:
@@ -66,7 +69,7 @@ def test_port_matches_golden_digests(name):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["cav2d_64", "chan3d_gz", "tunnel3d", "cyl2d"])
+@pytest.mark.parametrize("name", ["cav2d_64", "chan3d_gz", "tunnel3d", "cyl2d", "sliptunnel3d", "fevel2d", "fevel2d_tav", "pleft3d_tav"])
 def test_port_matches_compiled_reference_arrays(name):
     if port.ref_binary(name) is None:
         pytest.skip("oracle/_ref/luma_ref_%s not built here" % name)
@@ -76,13 +79,13 @@ def test_port_matches_compiled_reference_arrays(name):
     g = port.PortGrid(case)
     init = ref["init"]
     assert np.array_equal(init["lattyp"], g.lattyp)
-    bc = np.isin(g.lattyp, (6, 7))
+    bc = np.isin(g.lattyp, (6, 7, 8))
     assert np.array_equal(init["wall"].reshape(-1, 5)[bc], g.wall.reshape(-1, 5)[bc])
     assert np.array_equal(init["f"], g.f)
     for s in steps:
         g.step(s - g.t)
         d = ref["t%d" % s]
-        for nm in ("f", "rho", "u"):
+        for nm in ("f", "rho", "u") + (("rho_timeav", "ui_timeav", "uiuj_timeav") if case.time_averaged else ()):
             a, b = d[nm], getattr(g, nm)
             assert np.array_equal(a, b), "%s t=%d %s: %d sites differ, first at %d" % (
                 name, s, nm, int((a != b).sum()), int(np.flatnonzero(a != b)[0]))
