@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LUMA_B200_ABI_VERSION 1
+#define LUMA_B200_ABI_VERSION 2
 
 /* ---- status codes (luma_b200_strerror gives the text; the shim maps non-zero to L_ERROR,
  *      inc/stdafx.h:135-149) ---- */
@@ -57,7 +57,8 @@ enum {
 };
 
 /* eType values the path understands (inc/Enumerations.h:84-96) */
-enum { LUMA_E_SOLID = 0, LUMA_E_FLUID = 1, LUMA_E_REFINED = 2, LUMA_E_VELOCITY = 6, LUMA_E_PRESSURE = 7 };
+enum { LUMA_E_SOLID = 0, LUMA_E_FLUID = 1, LUMA_E_REFINED = 2, LUMA_E_VELOCITY = 6, LUMA_E_PRESSURE = 7,
+       LUMA_E_SLIP = 8, LUMA_E_EXTRAPOLATE_RIGHT = 9 };
 
 typedef struct luma_b200 luma_b200_t;
 
@@ -73,7 +74,7 @@ typedef struct LumaCaseParams {
 	int32_t  x_offset, x_count; /* first owned global x-plane and number of owned planes
 	                               (luma_b200_slab gives the reference's uniform split) */
 	int32_t  device;            /* CUDA device ordinal for this process */
-	int32_t  regularised;       /* L_REGULARISED_BOUNDARIES (only 1 is supported on the BC path) */
+	int32_t  regularised;       /* L_REGULARISED_BOUNDARIES; 0 = forced-equilibrium velocity BC (optimised.cpp:254-270) */
 	int32_t  bgksmag;           /* L_USE_BGKSMAG */
 	double   csmag;             /* L_CSMAG */
 	int32_t  gravity_on;        /* L_GRAVITY_ON */
@@ -89,9 +90,10 @@ typedef struct LumaCaseParams {
 	double   reynolds_ramp;     /* L_REYNOLDS_RAMP */
 	double   re;                /* L_RE (only read with reynolds_ramp_on) */
 	int32_t  t;                 /* GridObj::t, completed iterations at upload time */
+	int32_t  time_averaged;     /* L_COMPUTE_TIME_AVERAGED_QUANTITIES (optimised.cpp:895-917) */
 } LumaCaseParams;
 
-/* Wall descriptor of one velocity/pressure site, exactly what GridUtils::isWithinDomainWall
+/* Wall descriptor of one velocity/pressure/slip site, exactly what GridUtils::isWithinDomainWall
  * (src/GridUtils.cpp:1369-1430) returns for it.  `site` indexes the arrays passed to upload. */
 typedef struct LumaSiteBC {
 	int64_t site;
@@ -189,6 +191,13 @@ int  luma_b200_step(luma_b200_t *h, int32_t nsteps);
 int  luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what,
                         double *f_aos, double *rho, double *u_aos);
 int  luma_b200_download_lattyp(luma_b200_t *h, int32_t halo, int32_t *lattyp);
+
+/* ---- time-averaged statistics (handles created with time_averaged = 1): rho_timeav [cells],
+ *      ui_timeav [cells*D], uiuj_timeav [cells*(3D-3)], the reference's arrays (inc/GridObj.h:93-95,
+ *      written by io_hdf5 / io_lite).  They start at zero (init_grids.cpp:304-306); upload_timeav lets a
+ *      host that kept them across a restart hand them back.  NULL pointers are skipped. ---- */
+int  luma_b200_download_timeav(luma_b200_t *h, int32_t halo, double *rho_timeav, double *ui_timeav, double *uiuj_timeav);
+int  luma_b200_upload_timeav(luma_b200_t *h, int32_t halo, const double *rho_timeav, const double *ui_timeav, const double *uiuj_timeav);
 
 /* ---- scalars the host object keeps in step with the device (GridObj::t, ::omega, ::nu) ---- */
 int  luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu);

@@ -5,8 +5,9 @@ Python here is plumbing and the host-side mirror of the reference's interface (D
 inc/definitions.h, GridObj ~ inc/GridObj.h); all lattice arithmetic is in luma_b200/csrc/*.cu.
 There is no CPU fallback: without the built CUDA library, or without a GPU, calls fail loudly.
 """
-from .definitions import Definitions, eFluid, ePressure, eSolid, eVelocity  # noqa: F401
+from .definitions import Definitions, eExtrapolateRight, eFluid, ePressure, eSlip, eSolid, eVelocity  # noqa: F401
 from .gridobj import GridObj, comm_unique_id  # noqa: F401
 from . import capi  # noqa: F401
 
-__all__ = ["Definitions", "GridObj", "comm_unique_id", "capi", "eSolid", "eFluid", "eVelocity", "ePressure"]
+__all__ = ["Definitions", "GridObj", "comm_unique_id", "capi", "eSolid", "eFluid", "eVelocity", "ePressure", "eSlip",
+           "eExtrapolateRight"]

@@ -13,7 +13,7 @@ from . import build as _build
 # status codes (include/luma_b200.h)
 OK, EINVAL, ECUDA, ENCCL, ENOMEM, EUNSUPPORTED, ESTATE, EBC_NOT_WALL, EBC_PRESSURE_EDGE, EBC_OFFGRID = range(10)
 # eType (inc/Enumerations.h:84-96)
-E_SOLID, E_FLUID, E_REFINED, E_VELOCITY, E_PRESSURE = 0, 1, 2, 6, 7
+E_SOLID, E_FLUID, E_REFINED, E_VELOCITY, E_PRESSURE, E_SLIP, E_EXTRAPOLATE_RIGHT = 0, 1, 2, 6, 7, 8, 9
 F, RHO, U = 1, 2, 4
 
 
@@ -29,7 +29,7 @@ class LumaCaseParams(C.Structure):
         ("omega", C.c_double),
         ("velocity_ramp_on", C.c_int32), ("velocity_ramp", C.c_double),
         ("reynolds_ramp_on", C.c_int32), ("reynolds_ramp", C.c_double), ("re", C.c_double),
-        ("t", C.c_int32),
+        ("t", C.c_int32), ("time_averaged", C.c_int32),
     ]
 
 
@@ -105,6 +105,8 @@ def load(build_if_missing: bool = True):
     L.luma_b200_step.argtypes = [H, C.c_int32]
     L.luma_b200_download.argtypes = [H, C.c_int32, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
     L.luma_b200_download_lattyp.argtypes = [H, C.c_int32, C.c_void_p]
+    L.luma_b200_download_timeav.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.luma_b200_upload_timeav.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.luma_b200_get_time.argtypes = [H, _ip, _dp, _dp]
     L.luma_b200_forces.argtypes = [H, _dp]
     L.luma_b200_stats.argtypes = [H, C.POINTER(LumaStats)]
@@ -113,9 +115,9 @@ def load(build_if_missing: bool = True):
     L.luma_b200_halo_plan.argtypes = [C.POINTER(LumaCaseParams), C.POINTER(LumaHaloMsg), C.c_int32, _ip]
     L.luma_b200_selftest_div_const.argtypes = [C.c_int32, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     for nm in ("create", "slab", "comm_unique_id", "comm_init", "upload", "init_synthetic", "step", "download",
-               "download_lattyp", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
+               "download_lattyp", "download_timeav", "upload_timeav", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
         getattr(L, "luma_b200_" + nm).restype = C.c_int
-    if L.luma_b200_abi_version() != 1:
+    if L.luma_b200_abi_version() != 2:
         raise ImportError("libluma_b200.so ABI version mismatch")
     _lib = L
     return L

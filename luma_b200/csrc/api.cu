@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 #include <dlfcn.h>
 #include <cuda_runtime.h>
@@ -66,8 +68,13 @@ struct luma_b200
 	uint32_t *bcdesc = nullptr;
 	uint8_t *types = nullptr;
 	double *rho = nullptr, *u = nullptr, *uin = nullptr;
-	long long *bc_list = nullptr;
+	long long *bc_list = nullptr;   // sites k_bc handles (classes 2, 3, 4), ascending
+	int *bc_extra = nullptr;        // per entry: extra advances of the time averages (reference quirk), or null
 	int n_bc = 0;
+	long long *vel_list = nullptr;  // forced-equilibrium eVelocity sites whose stored u follows the ramp
+	int n_vel = 0;
+	bool general = false;           // the grid holds eSlip / eExtrapolateRight / forced-equilibrium sources
+	double *tav = nullptr;          // time-averaged statistics, SoA [1 + D + 3D-3][stride]
 	void *staging = nullptr;
 	size_t staging_bytes = 0;
 	double *momex_dev = nullptr;
@@ -208,6 +215,7 @@ static void free_all(luma_b200_t *h)
 	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
 	cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->cw); cudaFree(h->bcdesc); cudaFree(h->types);
 	cudaFree(h->rho); cudaFree(h->u); cudaFree(h->uin); cudaFree(h->bc_list); cudaFree(h->staging); cudaFree(h->momex_dev);
+	cudaFree(h->bc_extra); cudaFree(h->vel_list); cudaFree(h->tav);
 	if (h->ev_edge) cudaEventDestroy(h->ev_edge);
 	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -274,10 +282,13 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	if (e == cudaSuccess) e = cudaMalloc(&h->u, (size_t)h->stride * h->D * sizeof(double));
 	if (e == cudaSuccess) e = cudaMalloc(&h->uin, (size_t)3 * p->M * sizeof(double));
 	if (e == cudaSuccess) e = cudaMalloc(&h->momex_dev, (size_t)3 * 4096 * sizeof(double));
+	const size_t tav_bytes = (size_t)h->stride * (1 + h->D + 3 * h->D - 3) * sizeof(double);
+	if (e == cudaSuccess && p->time_averaged) e = cudaMalloc(&h->tav, tav_bytes);
 	if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return LUMA_B200_ENOMEM; }
 	CK(cudaMemsetAsync(h->cw, 0, (size_t)h->cells * sizeof(uint32_t), h->s_main));
 	CK(cudaMemsetAsync(h->bcdesc, 0, (size_t)h->cells * sizeof(uint32_t), h->s_main));
 	CK(cudaMemsetAsync(h->uin, 0, (size_t)3 * p->M * sizeof(double), h->s_main));
+	if (h->tav) CK(cudaMemsetAsync(h->tav, 0, tav_bytes, h->s_main));      // init_grids.cpp:304-306
 	CK(cudaStreamSynchronize(h->s_main));
 	return LUMA_B200_OK;
 }
@@ -369,28 +380,45 @@ static int exchange_populations(luma_b200_t *h, double *lat, cudaStream_t s)
 	return LUMA_B200_OK;
 }
 
-static int exchange_types(luma_b200_t *h, cudaStream_t s)
+// one-off, when the geometry is finalised: the ghost planes' eType, wall descriptors, rho and u (what a
+// site on a slab face needs to know about the sites it pulls from in the neighbouring slab)
+static int exchange_ghost_planes(luma_b200_t *h, cudaStream_t s)
 {
 	const int n = h->p.nranks, right = (h->p.rank + 1) % n, left = (h->p.rank - 1 + n) % n;
 	const size_t cnt = (size_t)h->MK;
+	const long long lo_own = h->MK, hi_own = (long long)(h->P - 2) * h->MK, lo_gh = 0, hi_gh = (long long)(h->P - 1) * h->MK;
 	NK(g_nccl.GroupStart());
-	NK(g_nccl.Send(h->types + (long long)(h->P - 2) * h->MK, cnt, ncclUint8, right, h->comm, s));
-	NK(g_nccl.Recv(h->types, cnt, ncclUint8, left, h->comm, s));
-	NK(g_nccl.Send(h->types + h->MK, cnt, ncclUint8, left, h->comm, s));
-	NK(g_nccl.Recv(h->types + (long long)(h->P - 1) * h->MK, cnt, ncclUint8, right, h->comm, s));
+	NK(g_nccl.Send(h->types + hi_own, cnt, ncclUint8, right, h->comm, s));
+	NK(g_nccl.Recv(h->types + lo_gh, cnt, ncclUint8, left, h->comm, s));
+	NK(g_nccl.Send(h->types + lo_own, cnt, ncclUint8, left, h->comm, s));
+	NK(g_nccl.Recv(h->types + hi_gh, cnt, ncclUint8, right, h->comm, s));
+	NK(g_nccl.Send(h->bcdesc + hi_own, cnt, ncclUint32, right, h->comm, s));
+	NK(g_nccl.Recv(h->bcdesc + lo_gh, cnt, ncclUint32, left, h->comm, s));
+	NK(g_nccl.Send(h->bcdesc + lo_own, cnt, ncclUint32, left, h->comm, s));
+	NK(g_nccl.Recv(h->bcdesc + hi_gh, cnt, ncclUint32, right, h->comm, s));
+	for (int d = -1; d < h->D; ++d)
+	{
+		double *q = (d < 0) ? h->rho : h->u + (long long)d * h->stride;
+		NK(g_nccl.Send(q + hi_own, cnt, ncclFloat64, right, h->comm, s));
+		NK(g_nccl.Recv(q + lo_gh, cnt, ncclFloat64, left, h->comm, s));
+		NK(g_nccl.Send(q + lo_own, cnt, ncclFloat64, left, h->comm, s));
+		NK(g_nccl.Recv(q + hi_gh, cnt, ncclFloat64, right, h->comm, s));
+	}
 	NK(g_nccl.GroupEnd());
 	return LUMA_B200_OK;
 }
 
-// after h->types (owned planes) and h->bcdesc exist on the device: ghost types, validation of the
-// boundary sites the way the reference would L_ERROR on them, boundary list, cell words.
+static inline int lat_c(int Q, int v, int d) { return (Q == 19) ? D3Q19::c(v, d) : D2Q9::c(v, d); }
+
+// after h->types (owned planes) and h->bcdesc exist on the device: ghost planes, validation of the
+// boundary sites the way the reference would L_ERROR on them, the list of sites k_bc handles, cell words.
 static int finalize_geometry(luma_b200_t *h)
 {
 	const LumaCaseParams &p = h->p;
 	if (h->ghost)
 	{
 		if (!h->comm) FAIL(LUMA_B200_ESTATE, "nranks > 1 needs luma_b200_comm_init before upload/init");
-		int rc = exchange_types(h, h->s_main);
+		int rc = exchange_ghost_planes(h, h->s_main);
 		if (rc) return rc;
 	}
 	std::vector<uint8_t> types((size_t)h->cells);
@@ -399,59 +427,160 @@ static int finalize_geometry(luma_b200_t *h)
 	CK(cudaMemcpyAsync(desc.data(), h->bcdesc, (size_t)h->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
 
-	std::vector<long long> list;
-	const int pb = h->ghost, pe = h->P - h->ghost;
-	for (int pl = pb; pl < pe; ++pl)
+	const int P = h->P, M = p.M, K = p.K, Q = h->Q, D = h->D;
+	const int pb = h->ghost, pe = P - h->ghost;
+	const bool wrap = h->ghost == 0, reg = p.regularised != 0;
+	auto site = [&](int pl, int j, int k) { return ((long long)pl * M + j) * K + k; };
+	auto never_streamed = [&](uint8_t t) { return t == T_SOLID || t == T_REFINED || (t == T_VELOCITY && !reg); };   // optimised.cpp:91-95
+
+	std::vector<long long> list;                 // sites k_bc handles
+	std::vector<long long> forced;               // eFluid sites that must be handled per link (class 4)
+	std::vector<std::pair<long long, int>> extra; // (site, extra advances of its time averages per step)
+	std::vector<long long> vel;                  // forced-equilibrium eVelocity sites (their stored u follows the ramp)
+	bool general = false;
+
+	for (int pl = 0; pl < P; ++pl)
 	{
-		for (int j = 0; j < p.M; ++j)
-			for (int k = 0; k < p.K; ++k)
+		const bool owned = pl >= pb && pl < pe;
+		const uint8_t *row = &types[(size_t)pl * M * K];
+		for (int j = 0; j < M; ++j)
+			for (int k = 0; k < K; ++k)
 			{
-				const long long id = ((long long)pl * p.M + j) * p.K + k;
-				const uint8_t t = types[(size_t)id];
-				if (t == LUMA_E_SOLID || t == LUMA_E_FLUID) continue;
-				if (t != LUMA_E_VELOCITY && t != LUMA_E_PRESSURE)
-					FAIL(LUMA_B200_EUNSUPPORTED, "site type " + std::to_string((int)t) + " (refinement/BFL/slip/extrapolation) is outside the level-0 path");
-				if (!p.regularised)
-					FAIL(LUMA_B200_EUNSUPPORTED, "velocity/pressure sites need L_REGULARISED_BOUNDARIES on this path");
+				const uint8_t t = row[(size_t)j * K + k];
+				if (t == T_SOLID || t == T_FLUID) continue;
+				const long long id = site(pl, j, k);
+				if (t != T_VELOCITY && t != T_PRESSURE && t != T_SLIP && t != T_EXTRAPOLATE_RIGHT)
+					FAIL(LUMA_B200_EUNSUPPORTED, "site type " + std::to_string((int)t) + " (refinement/BFL) is outside the level-0 path");
+
+				// sites that pull from an eExtrapolateRight or forced-equilibrium eVelocity site take the per-link path
+				if (t == T_EXTRAPOLATE_RIGHT || (t == T_VELOCITY && !reg))
+				{
+					general = true;
+					for (int v = 0; v < Q; ++v)
+					{
+						int dp = pl + lat_c(Q, v, 0), dj = j + lat_c(Q, v, 1), dk = k + lat_c(Q, v, 2);
+						if (wrap) dp = (dp + P) % P;
+						if (dp < pb || dp >= pe) continue;
+						dj = (dj + M) % M; dk = (dk + K) % K;
+						const uint8_t dt = types[(size_t)site(dp, dj, dk)];
+						if (never_streamed(dt)) continue;
+						if (t == T_EXTRAPOLATE_RIGHT && pl - 2 < pb)
+						{
+							// optimised.cpp:249-250 reads two planes to the left of the source
+							if (h->ghost) FAIL(LUMA_B200_EUNSUPPORTED, "an eExtrapolateRight site needs two planes to its left inside the same slab (slab too thin, or the site is reached through the periodic wrap)");
+							FAIL(LUMA_B200_EBC_OFFGRID, "eExtrapolateRight site within two planes of the low x end: the reference reads off the array");
+						}
+						if (dt == T_FLUID) forced.push_back(site(dp, dj, dk));
+					}
+				}
+				if (!owned) continue;
+
+				if (t == T_SLIP)
+				{
+					general = true;
+					if ((desc[(size_t)id] >> CW_EC_SHIFT) == 0)
+						FAIL(LUMA_B200_EBC_NOT_WALL, "Slip wall not located inside a domain wall region. Not currently supported.");   // optimised.cpp:577
+					list.push_back(id);
+					continue;
+				}
+				if (t == T_EXTRAPOLATE_RIGHT) { list.push_back(id); continue; }
+				if (!reg)
+				{
+					// non-regularised build: ePressure sites stream and collide with their stored rho,u; eVelocity sites are skipped
+					if (t == T_PRESSURE) { general = true; list.push_back(id); }
+					else vel.push_back(id);
+					continue;
+				}
+
+				// regularised velocity / pressure site (optimised.cpp:313-510)
 				const uint32_t d = desc[(size_t)id];
 				const int ec = (int)(d >> CW_EC_SHIFT);
 				if (ec == 0) FAIL(LUMA_B200_EBC_NOT_WALL, luma_b200_strerror(LUMA_B200_EBC_NOT_WALL));
-				if (ec > 1 && t == LUMA_E_PRESSURE) FAIL(LUMA_B200_EBC_PRESSURE_EDGE, luma_b200_strerror(LUMA_B200_EBC_PRESSURE_EDGE));
-				if (ec > 1 || t == LUMA_E_PRESSURE)
+				if (ec > 1 && t == T_PRESSURE) FAIL(LUMA_B200_EBC_PRESSURE_EDGE, luma_b200_strerror(LUMA_B200_EBC_PRESSURE_EDGE));
+				if (ec > 1 || t == T_PRESSURE)
 				{
 					int n[3];
 					for (int a = 0; a < 3; ++a) n[a] = (int)((d >> (CW_N_SHIFT + 2 * a)) & 3u) - 1;
+					const int ncalls = (t == T_PRESSURE) ? D - 1 : 1;      // one _LBM_updateAndExtrapolate per extrapolated quantity
 					for (int m = 1; m <= 2; ++m)
 					{
 						const int gi = p.x_offset + (pl - h->ghost) + m * n[0], jj = j + m * n[1], kk = k + m * n[2];
-						if (gi < 0 || gi >= p.N || jj < 0 || jj >= p.M || kk < 0 || kk >= p.K)
+						if (gi < 0 || gi >= p.N || jj < 0 || jj >= M || kk < 0 || kk >= K)
 							FAIL(LUMA_B200_EBC_OFFGRID, luma_b200_strerror(LUMA_B200_EBC_OFFGRID));
 						const int pp = pl + m * n[0];
 						if (pp < pb || pp >= pe)
 							FAIL(LUMA_B200_EUNSUPPORTED, "slab too thin: a boundary site extrapolates from a plane owned by another rank");
-						const uint8_t tn = types[(size_t)(((long long)pp * p.M + jj) * p.K + kk)];
-						if (tn != LUMA_E_SOLID && tn != LUMA_E_FLUID)
+						const long long idn = site(pp, jj, kk);
+						const uint8_t tn = types[(size_t)idn];
+						if (tn != T_SOLID && tn != T_FLUID)
 							FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from another boundary site (loop-order dependent in the reference)");
+						if (idn > id)
+						{
+							// the reference streams + macros this neighbour early (optimised.cpp:1375-1404)
+							if (tn == T_SOLID)
+								FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from an eSolid site with a larger index (the reference streams into that solid site)");
+							if (p.time_averaged) { extra.push_back({ idn, ncalls }); forced.push_back(idn); }
+						}
 					}
 				}
 				list.push_back(id);
 			}
 	}
+
+	// class-4 fluid sites join the list; the list is kept in ascending site order
+	std::sort(forced.begin(), forced.end());
+	forced.erase(std::unique(forced.begin(), forced.end()), forced.end());
+	list.insert(list.end(), forced.begin(), forced.end());
+	std::sort(list.begin(), list.end());
+	std::vector<int> extra_by_entry;
+	if (!extra.empty())
+	{
+		extra_by_entry.assign(list.size(), 0);
+		for (const auto &e : extra)
+		{
+			const size_t at = (size_t)(std::lower_bound(list.begin(), list.end(), e.first) - list.begin());
+			extra_by_entry[at] += e.second;
+		}
+	}
+	h->general = general || !forced.empty();
+
 	cudaFree(h->bc_list); h->bc_list = nullptr;
+	cudaFree(h->bc_extra); h->bc_extra = nullptr;
+	cudaFree(h->vel_list); h->vel_list = nullptr;
 	h->n_bc = (int)list.size();
+	h->n_vel = (!reg && p.velocity_ramp_on) ? (int)vel.size() : 0;
+	long long *forced_dev = nullptr;
 	if (h->n_bc)
 	{
 		if (cudaMalloc(&h->bc_list, list.size() * sizeof(long long)) != cudaSuccess) FAIL(LUMA_B200_ENOMEM, "bc list");
 		CK(cudaMemcpyAsync(h->bc_list, list.data(), list.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s_main));
 	}
+	if (!extra_by_entry.empty())
+	{
+		if (cudaMalloc(&h->bc_extra, extra_by_entry.size() * sizeof(int)) != cudaSuccess) FAIL(LUMA_B200_ENOMEM, "bc extra");
+		CK(cudaMemcpyAsync(h->bc_extra, extra_by_entry.data(), extra_by_entry.size() * sizeof(int), cudaMemcpyHostToDevice, h->s_main));
+	}
+	if (h->n_vel)
+	{
+		if (cudaMalloc(&h->vel_list, vel.size() * sizeof(long long)) != cudaSuccess) FAIL(LUMA_B200_ENOMEM, "velocity-site list");
+		CK(cudaMemcpyAsync(h->vel_list, vel.data(), vel.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s_main));
+	}
+	if (!forced.empty())
+	{
+		if (cudaMalloc(&forced_dev, forced.size() * sizeof(long long)) != cudaSuccess) FAIL(LUMA_B200_ENOMEM, "class-4 list");
+		CK(cudaMemcpyAsync(forced_dev, forced.data(), forced.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s_main));
+	}
 	GeomArgs g;
 	g.types = h->types; g.bcdesc = h->bcdesc; g.cw = h->cw;
 	g.P = h->P; g.M = p.M; g.K = p.K; g.wrap_x = h->ghost ? 0 : 1;
 	g.p_begin = pb; g.p_end = pe;
+	g.regularised = reg ? 1 : 0;
 	if (h->Q == 19) launch_cell_words<D3Q19>(g, h->s_main); else launch_cell_words<D2Q9>(g, h->s_main);
 	h->st.kernel_launches++;
-	CK(cudaGetLastError());
-	CK(cudaStreamSynchronize(h->s_main));
+	if (!forced.empty()) { launch_force_general(h->cw, forced_dev, (int)forced.size(), h->s_main); h->st.kernel_launches++; }
+	const cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(h->s_main);
+	cudaFree(forced_dev);
+	CK(e1); CK(e2);
 	return LUMA_B200_OK;
 }
 
@@ -543,8 +672,8 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	for (int a = 0; a < 6; ++a)
 	{
 		const int t = c->wall_type[a];
-		if (t != LUMA_E_SOLID && t != LUMA_E_FLUID && t != LUMA_E_VELOCITY && t != LUMA_E_PRESSURE)
-			FAIL(LUMA_B200_EUNSUPPORTED, "wall type outside {eSolid,eFluid,eVelocity,ePressure}");
+		if (t != LUMA_E_SOLID && t != LUMA_E_FLUID && t != LUMA_E_VELOCITY && t != LUMA_E_PRESSURE && t != LUMA_E_SLIP && t != LUMA_E_EXTRAPOLATE_RIGHT)
+			FAIL(LUMA_B200_EUNSUPPORTED, "wall type outside {eSolid,eFluid,eVelocity,ePressure,eSlip,eExtrapolateRight}");
 		if (c->wall_cells[a] < 0) FAIL(LUMA_B200_EINVAL, "negative wall thickness");
 	}
 	std::vector<double> uin((size_t)3 * p.M);
@@ -606,8 +735,11 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		const int cz = (h->Q == 19) ? D3Q19::c(v, 2) : D2Q9::c(v, 2);
 		a.off_pull[v] = 8LL * ((long long)v * h->stride - ((long long)cx * h->MK + (long long)cy * p.K + cz));
 	}
-	a.bc_list = h->bc_list; a.n_bc = h->n_bc; a.uin = h->uin;
+	a.bc_list = h->bc_list; a.bc_extra = h->bc_extra; a.n_bc = h->n_bc; a.uin = h->uin;
 	a.rho_out = p.rho_out;
+	a.types = h->types; a.general = h->general ? 1 : 0; a.regularised = p.regularised ? 1 : 0;
+	a.velramp_on = p.velocity_ramp_on ? 1 : 0;
+	a.tav = h->tav;
 	// force_xyz = rho_init * gravity * refinement_ratio along L_GRAVITY_DIRECTION (init_grids.cpp:296-297)
 	for (int d = 0; d < 3; ++d) { a.F[d] = 0.0; a.hF[d] = 0.0; }
 	if (force) { a.F[p.gravity_dir] = p.rhoin * p.gravity * 1.0; a.hF[p.gravity_dir] = 0.5 * a.F[p.gravity_dir]; }
@@ -631,6 +763,8 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		x.tau = 1.0 / h->omega;
 		for (int k = 0; k < 3; ++k) x.lam[k] = (1 - 0.5 * h->omega) * (h->C.w[k] / h->C.cs2);
 		x.ramp = velocity_ramp_coef(p, (t_now + 1) * p.dt);
+		x.ramp_t = velocity_ramp_coef(p, t_now * p.dt);
+		x.t_now = (double)t_now; x.t_next = (double)(t_now + 1);
 	};
 
 	int s = 0;
@@ -665,6 +799,16 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 			CK(cudaEventRecord(h->ev_comm, h->s_comm));
 			if (h->Q == 19) main_kernel<D3Q19>(h, in, smag, force, owned - 2);
 			else main_kernel<D2Q9>(h, in, smag, force, owned - 2);
+		}
+		if (a.write_macro && h->n_vel)
+		{
+			// stored u of the forced-equilibrium inlet sites as the reference leaves it after this step
+			VelSrcArgs vs;
+			vs.list = h->vel_list; vs.n = h->n_vel; vs.types = h->types; vs.bcdesc = h->bcdesc; vs.u = h->u; vs.stride = h->stride;
+			vs.uin = h->uin; vs.ramp_t = a.ramp_t;
+			vs.P = h->P; vs.M = p.M; vs.K = p.K; vs.N = p.N; vs.wrap_x = a.wrap_x; vs.x_first = p.x_offset - h->ghost;
+			if (h->Q == 19) launch_velsrc<D3Q19>(vs, h->s_main, &h->st.kernel_launches);
+			else launch_velsrc<D2Q9>(vs, h->s_main, &h->st.kernel_launches);
 		}
 		h->cur ^= 1;
 		++h->t;
@@ -728,6 +872,65 @@ int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_ao
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(h->s_main));
 	return LUMA_B200_OK;
+}
+
+// rho_timeav [cells], ui_timeav [cells*D], uiuj_timeav [cells*(3D-3)] in the reference's AoS layout (inc/GridObj.h:93-95)
+static int transfer_timeav(luma_b200_t *h, int32_t halo, double *rho_tav, double *ui_tav, double *uiuj_tav, bool to_host)
+{
+	if (!h->tav) FAIL(LUMA_B200_ESTATE, "the handle was created without time_averaged");
+	if (halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "timeav: halo");
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const long long owned = (long long)p.x_count * h->MK;
+	const long long host_off = (long long)halo * h->MK, dev_off = (long long)h->ghost * h->MK;
+	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(192u << 20) / (h->Q * 8)));
+	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
+	if (rc) return rc;
+	if (rho_tav)
+	{
+		if (to_host) CK(cudaMemcpyAsync(rho_tav + host_off, h->tav + dev_off, (size_t)owned * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+		else CK(cudaMemcpyAsync(h->tav + dev_off, rho_tav + host_off, (size_t)owned * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+	}
+	double *host[2] = { ui_tav, uiuj_tav };
+	const int ncomp[2] = { h->D, 3 * h->D - 3 }, slot[2] = { 1, 1 + h->D };
+	for (int a = 0; a < 2; ++a)
+	{
+		if (!host[a]) continue;
+		double *soa = h->tav + (long long)slot[a] * h->stride;
+		for (long long c0 = 0; c0 < owned; c0 += chunk)
+		{
+			const long long n = std::min(chunk, owned - c0);
+			double *hp = host[a] + (host_off + c0) * ncomp[a];
+			if (to_host)
+			{
+				launch_u_soa_to_aos(soa, (double *)h->staging, h->stride, ncomp[a], dev_off + c0, n, h->s_main);
+				CK(cudaMemcpyAsync(hp, h->staging, (size_t)n * ncomp[a] * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+			}
+			else
+			{
+				CK(cudaMemcpyAsync(h->staging, hp, (size_t)n * ncomp[a] * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+				launch_u_aos_to_soa((const double *)h->staging, soa, h->stride, ncomp[a], dev_off + c0, n, h->s_main);
+			}
+			h->st.kernel_launches++;
+		}
+	}
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(h->s_main));
+	return LUMA_B200_OK;
+}
+
+int luma_b200_download_timeav(luma_b200_t *h, int32_t halo, double *rho_timeav, double *ui_timeav, double *uiuj_timeav)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "download before upload/init_synthetic");
+	return transfer_timeav(h, halo, rho_timeav, ui_timeav, uiuj_timeav, true);
+}
+
+int luma_b200_upload_timeav(luma_b200_t *h, int32_t halo, const double *rho_timeav, const double *ui_timeav, const double *uiuj_timeav)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "upload_timeav before upload/init_synthetic");
+	return transfer_timeav(h, halo, const_cast<double *>(rho_timeav), const_cast<double *>(ui_timeav), const_cast<double *>(uiuj_timeav), false);
 }
 
 int luma_b200_download_lattyp(luma_b200_t *h, int32_t halo, int32_t *lattyp)

@@ -135,9 +135,108 @@ __device__ __forceinline__ void store_populations(const StepArgs &a, const long 
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-link stream of a site that is, or pulls from, one of the special types -- the full branch
+// ladder of GridObj::_LBM_stream_opt (optimised.cpp:206-297) evaluated from the eType array:
+// specular reflection on eSlip sites (_LBM_applySpecReflect_opt :527-581: the first direction, in the
+// order x, y, z, in which the link's component equals the inward normal's reflects the link),
+// halfway bounce-back (:238-243), eExtrapolateRight (:246-251: the same population two planes to the
+// left of the source), forced-equilibrium eVelocity (:254-270, non-regularised builds only), copy.
+// ------------------------------------------------------------------------------------------------
+template <class L>
+__device__ __noinline__ void pull_general(const StepArgs &a, const int p, const int j, const int k, const long long id,
+	const uint32_t w, const uint8_t type, double (&f)[L::Q])
+{
+	int n[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) n[d] = (int)((w >> (CW_N_SHIFT + 2 * d)) & 3u) - 1;
+	const double *fin = a.fin;
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		const int cx = L::c(v, 0), cy = L::c(v, 1), cz = L::c(v, 2);
+		if (type == T_SLIP)
+		{
+			if (cx != 0 && n[0] == cx) { f[v] = fin[(long long)reflect<L>(v, 0) * a.stride + id]; continue; }
+			if (cy != 0 && n[1] == cy) { f[v] = fin[(long long)reflect<L>(v, 1) * a.stride + id]; continue; }
+			if (L::D == 3 && cz != 0 && n[2] == cz) { f[v] = fin[(long long)reflect<L>(v, 2) * a.stride + id]; continue; }
+		}
+		int sp = p - cx, sj = j - cy, sk = k - cz;
+		if (a.wrap_x) { if (sp < 0) sp += a.P; else if (sp >= a.P) sp -= a.P; }
+		if (sj < 0) sj += a.M; else if (sj >= a.M) sj -= a.M;
+		if (sk < 0) sk += a.K; else if (sk >= a.K) sk -= a.K;
+		const long long src = ((long long)sp * a.M + sj) * a.K + sk;
+		const uint8_t st = a.types[src];
+		if (st == T_SOLID)
+			f[v] = fin[(long long)opposite<L>(v) * a.stride + id];
+		else if (st == T_EXTRAPOLATE_RIGHT)
+			f[v] = fin[(long long)v * a.stride + src - 2 * (long long)a.MK];
+		else if (!a.regularised && st == T_VELOCITY)
+		{
+			// u of the source site is u_in[j of THIS site] * ramp(t*dt) when a ramp is defined (:258-263)
+			double us[3] = { 0.0, 0.0, 0.0 }, feq[L::Q];
+#pragma unroll
+			for (int d = 0; d < L::D; ++d)
+				us[d] = a.velramp_on ? a.uin[d * a.M + j] * a.ramp_t : a.u[(long long)d * a.stride + src];
+			equilibrium_all<L>(a.rho[src], us, a.C, feq);
+			f[v] = feq[v];
+		}
+		else
+			f[v] = fin[(long long)v * a.stride + src];
+	}
+}
+
+// stream of a site handled by k_bc: the fast path unless the grid holds special types
+template <class L>
+__device__ __forceinline__ void pull_any(const StepArgs &a, const int p, const unsigned r, const int j, const int k,
+	const long long id, const uint32_t w, double (&f)[L::Q])
+{
+	if (a.general && cw_class(w) != CLS_FLUID) pull_general<L>(a, p, j, k, id, w, a.types[id], f);
+	else pull_populations<L>(a, p, r, id, w, f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// time-averaged statistics, the tail of GridObj::_LBM_macro_opt (optimised.cpp:895-917):
+//   avg = (avg * (double)t + x) / (double)(t + 1)   for rho, u_p and u_p*u_q (p <= q).
+// `reps` > 1 reproduces the reference advancing the averages of a site once more every time a
+// boundary site "updates it on the fly" (_LBM_updateInteriorLatticeSite :1422-1434 calls
+// _LBM_macro_opt, which ends with this block).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tavg_advance(double avg, const double x, const double t_now, const double t_next, const int reps)
+{
+	for (int r = 0; r < reps; ++r)
+	{
+		double ta = avg * t_now;
+		ta = ta + x;
+		avg = ta / t_next;
+	}
+	return avg;
+}
+
+template <class L>
+__device__ __forceinline__ void tavg_update(const StepArgs &a, const long long id, const double rho, const double (&u)[3], const int reps)
+{
+	double *t = a.tav + id;
+	t[0] = tavg_advance(t[0], rho, a.t_now, a.t_next, reps);
+	int pq = 0;
+#pragma unroll
+	for (int p = 0; p < L::D; ++p)
+	{
+		double *tp = t + (long long)(1 + p) * a.stride;
+		*tp = tavg_advance(*tp, u[p], a.t_now, a.t_next, reps);
+#pragma unroll
+		for (int q = p; q < L::D; ++q)
+		{
+			double *tq = t + (long long)(1 + L::D + pq) * a.stride;
+			*tq = tavg_advance(*tq, u[p] * u[q], a.t_now, a.t_next, reps);
+			++pq;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
 // ------------------------------------------------------------------------------------------------
-template <class L, bool SMAG, bool FORCE>
+template <class L, bool SMAG, bool FORCE, bool TAVG>
 __global__ void __launch_bounds__(STEP_THREADS, SMAG ? LUMA_MIN_BLOCKS_SMAG : LUMA_MIN_BLOCKS) k_step(const StepArgs a)
 {
 	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
@@ -150,6 +249,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SMAG ? LUMA_MIN_BLOCKS_SMAG : LU
 	double f[L::Q], feq[L::Q], u[3], rho;
 	pull_populations<L>(a, p, r, id, w, f);
 	macroscopic<L, FORCE>(f, a.hF, rho, u);
+	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
 	equilibrium_all<L>(rho, u, a.C, feq);
 	collide<L, SMAG, FORCE>(a, u, feq, f);
 	store_populations<L>(a, id, f);
@@ -170,10 +270,11 @@ __device__ __noinline__ void neighbour_macro(const StepArgs &a, const int p, con
 	const unsigned r = (unsigned)j * (unsigned)a.K + (unsigned)k;
 	const long long id = (long long)p * a.MK + r;
 	const uint32_t w = a.cw[id];
-	if (cw_class(w) == CLS_FLUID)
+	const uint32_t cls = cw_class(w);
+	if (cls == CLS_FLUID || cls == CLS_GENERAL)      // upload guarantees the neighbour is eFluid or eSolid
 	{
 		double f[L::Q];
-		pull_populations<L>(a, p, r, id, w, f);
+		pull_any<L>(a, p, r, j, k, id, w, f);
 		macroscopic<L, FORCE>(f, a.hF, rho, u);
 	}
 	else
@@ -297,7 +398,32 @@ __device__ __forceinline__ void bc_regularise(const StepArgs &a, const uint32_t 
 	collide<L, SMAG, FORCE>(a, uw, feq, f);
 }
 
-template <class L, bool SMAG, bool FORCE>
+// class-4 sites: stream per link, macro only for eFluid/eSlip (optimised.cpp:803-806; every other type
+// keeps its stored rho,u), force, collide
+template <class L, bool SMAG, bool FORCE, bool TAVG>
+__device__ __noinline__ void general_site(const StepArgs &a, const int p, const int j, const int k, const long long id,
+	const uint32_t w, const int reps)
+{
+	const uint8_t type = a.types[id];
+	double f[L::Q], feq[L::Q], u[3], rho;
+	pull_general<L>(a, p, j, k, id, w, type, f);
+	if (type == T_FLUID || type == T_SLIP) macroscopic<L, FORCE>(f, a.hF, rho, u);
+	else
+	{
+		rho = a.rho[id];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) u[d] = (d < L::D) ? a.u[(long long)d * a.stride + id] : 0.0;
+	}
+	if (TAVG) tavg_update<L>(a, id, rho, u, reps);
+	equilibrium_all<L>(rho, u, a.C, feq);
+	collide<L, SMAG, FORCE>(a, u, feq, f);
+	store_populations<L>(a, id, f);
+	a.rho[id] = rho;
+#pragma unroll
+	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
+}
+
+template <class L, bool SMAG, bool FORCE, bool TAVG>
 __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,9 +433,15 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 	const unsigned r = (unsigned)(id - (long long)p * a.MK);
 	const int j = (int)(r / (unsigned)a.K), k = (int)(r - (unsigned)j * (unsigned)a.K);
 	const uint32_t w = a.cw[id];
+	const int reps = 1 + ((TAVG && a.bc_extra) ? a.bc_extra[t] : 0);
+	if (cw_class(w) == CLS_GENERAL)
+	{
+		general_site<L, SMAG, FORCE, TAVG>(a, p, j, k, id, w, reps);
+		return;
+	}
 
 	double f[L::Q];
-	pull_populations<L>(a, p, r, id, w, f);
+	pull_any<L>(a, p, r, j, k, id, w, f);
 
 	double r1 = 0.0, r2 = 0.0, u1[3] = { 0.0, 0.0, 0.0 }, u2[3] = { 0.0, 0.0, 0.0 };
 	if (bc_needs_neighbours(w))
@@ -322,6 +454,7 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 	}
 	double dens, uw[3];
 	bc_regularise<L, SMAG, FORCE>(a, w, j, f, r1, u1, r2, u2, dens, uw);
+	if (TAVG) tavg_update<L>(a, id, dens, uw, reps);      // _LBM_macro_opt still runs its averaging tail for these types
 
 	a.rho[id] = dens;
 #pragma unroll
@@ -329,14 +462,97 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 	store_populations<L>(a, id, f);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forced-equilibrium velocity BC with L_VELOCITY_RAMP: every site that pulls from an eVelocity
+// site first overwrites that site's stored u with u_in[j of the PULLING site] * ramp (optimised.cpp:
+// 258-263), so what the array holds after a step is the value written by the LAST puller in the
+// reference's loop order (x slowest, then y, then z).  The populations never depend on the stored
+// value (every puller uses its own), so this kernel runs once, after the last step of a call.
+// ------------------------------------------------------------------------------------------------
+template <class L>
+__global__ void __launch_bounds__(64) k_velsrc(const VelSrcArgs a)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.n) return;
+	const long long MK = (long long)a.M * a.K;
+	const long long id = a.list[t];
+	const int p = (int)(id / MK);
+	const int r = (int)(id - (long long)p * MK);
+	const int j = r / a.K, k = r - j * a.K;
+	long long best = -1;
+	int best_j = 0;
+#pragma unroll
+	for (int v = 0; v < L::Q - 1; ++v)
+	{
+		const int cx = L::c(v, 0), cy = L::c(v, 1), cz = L::c(v, 2);
+		int dp = p + cx, dj = j + cy, dk = k + cz;
+		if (a.wrap_x) { if (dp < 0) dp += a.P; else if (dp >= a.P) dp -= a.P; }
+		else if (dp < 0 || dp >= a.P) continue;
+		if (dj < 0) dj += a.M; else if (dj >= a.M) dj -= a.M;
+		if (dk < 0) dk += a.K; else if (dk >= a.K) dk -= a.K;
+		const long long did = ((long long)dp * a.M + dj) * a.K + dk;
+		const uint8_t dt = a.types[did];
+		if (dt == T_SOLID || dt == T_REFINED || dt == T_VELOCITY) continue;      // never streamed (optimised.cpp:91-95)
+		if (dt == T_SLIP)
+		{
+			// a slip site reflects this link instead of pulling it (:229-233)
+			const uint32_t d = a.bcdesc[did];
+			const int n0 = (int)((d >> CW_N_SHIFT) & 3u) - 1, n1 = (int)((d >> (CW_N_SHIFT + 2)) & 3u) - 1, n2 = (int)((d >> (CW_N_SHIFT + 4)) & 3u) - 1;
+			if ((cx != 0 && n0 == cx) || (cy != 0 && n1 == cy) || (L::D == 3 && cz != 0 && n2 == cz)) continue;
+		}
+		int gx = (a.x_first + dp) % a.N;
+		if (gx < 0) gx += a.N;
+		const long long key = ((long long)gx * a.M + dj) * a.K + dk;
+		if (key > best) { best = key; best_j = dj; }
+	}
+	if (best >= 0)
+	{
+#pragma unroll
+		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = a.uin[d * a.M + best_j] * a.ramp_t;
+	}
+}
+
+template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches)
+{
+	if (a.n <= 0) return;
+	k_velsrc<L><<<(a.n + 63) / 64, 64, 0, s>>>(a);
+	if (launches) ++*launches;
+}
+
+// sites the host wants handled per link (class 4) although they are eFluid
+__global__ void k_force_general(uint32_t *cw, const long long *ids, int n)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const uint32_t w = cw[ids[t]];
+	if (cw_class(w) == CLS_FLUID) cw[ids[t]] = (w & ~(CW_CLASS_MASK << CW_CLASS_SHIFT)) | (CLS_GENERAL << CW_CLASS_SHIFT);
+}
+void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_t s)
+{
+	if (n > 0) k_force_general<<<(n + 127) / 128, 128, 0, s>>>(cw, ids, n);
+}
+
+#define LUMA_DISPATCH(KERNEL, GRID, THREADS) \
+	do { \
+		const int key = (smag ? 4 : 0) | (force ? 2 : 0) | (a.tav ? 1 : 0); \
+		switch (key) \
+		{ \
+		case 0: KERNEL<L, false, false, false><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 1: KERNEL<L, false, false, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 2: KERNEL<L, false, true, false><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 3: KERNEL<L, false, true, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 4: KERNEL<L, true, false, false><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 5: KERNEL<L, true, false, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 6: KERNEL<L, true, true, false><<<GRID, THREADS, 0, s>>>(a); break; \
+		default: KERNEL<L, true, true, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		} \
+	} while (0)
+
 template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches)
 {
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
-	if (smag && force) k_step<L, true, true><<<grid, STEP_THREADS, 0, s>>>(a);
-	else if (smag) k_step<L, true, false><<<grid, STEP_THREADS, 0, s>>>(a);
-	else if (force) k_step<L, false, true><<<grid, STEP_THREADS, 0, s>>>(a);
-	else k_step<L, false, false><<<grid, STEP_THREADS, 0, s>>>(a);
+	LUMA_DISPATCH(k_step, grid, STEP_THREADS);
 	if (launches) ++*launches;
 }
 
@@ -345,10 +561,7 @@ template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cuda
 	if (a.n_bc <= 0) return;
 	const int threads = 64;
 	dim3 grid((a.n_bc + threads - 1) / threads);
-	if (smag && force) k_bc<L, true, true><<<grid, threads, 0, s>>>(a);
-	else if (smag) k_bc<L, true, false><<<grid, threads, 0, s>>>(a);
-	else if (force) k_bc<L, false, true><<<grid, threads, 0, s>>>(a);
-	else k_bc<L, false, false><<<grid, threads, 0, s>>>(a);
+	LUMA_DISPATCH(k_bc, grid, threads);
 	if (launches) ++*launches;
 }
 
@@ -366,7 +579,10 @@ __global__ void k_cell_words(const GeomArgs g)
 	const long long id = (long long)p * MK + r;
 	const uint8_t t = g.types[id];
 	uint32_t cls = CLS_SKIP;
-	if (t == 1) cls = CLS_FLUID; else if (t == 6) cls = CLS_VELOCITY; else if (t == 7) cls = CLS_PRESSURE;
+	if (t == T_FLUID) cls = CLS_FLUID;
+	else if (t == T_VELOCITY) cls = g.regularised ? CLS_VELOCITY : CLS_SKIP;      // optimised.cpp:91-95
+	else if (t == T_PRESSURE) cls = g.regularised ? CLS_PRESSURE : CLS_GENERAL;
+	else if (t == T_SLIP || t == T_EXTRAPOLATE_RIGHT) cls = CLS_GENERAL;
 	uint32_t w = 0;
 	if (cls != CLS_SKIP)
 	{
@@ -519,16 +735,18 @@ template <class L> void launch_soa_to_aos(const double *soa, double *aos, long l
 {
 	if (n > 0) k_soa_to_aos<L::Q><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(soa, aos, stride, first, n);
 }
-void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int D, long long first, long long n, cudaStream_t s)
+void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int ncomp, long long first, long long n, cudaStream_t s)
 {
 	if (n <= 0) return;
-	if (D == 3) k_aos_to_soa<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(aos, soa, stride, first, n);
+	if (ncomp == 6) k_aos_to_soa<6><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(aos, soa, stride, first, n);
+	else if (ncomp == 3) k_aos_to_soa<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(aos, soa, stride, first, n);
 	else k_aos_to_soa<2><<<(unsigned)((n + 63) / 64), 128, 0, s>>>(aos, soa, stride, first, n);
 }
-void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int D, long long first, long long n, cudaStream_t s)
+void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int ncomp, long long first, long long n, cudaStream_t s)
 {
 	if (n <= 0) return;
-	if (D == 3) k_soa_to_aos<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(soa, aos, stride, first, n);
+	if (ncomp == 6) k_soa_to_aos<6><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(soa, aos, stride, first, n);
+	else if (ncomp == 3) k_soa_to_aos<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(soa, aos, stride, first, n);
 	else k_soa_to_aos<2><<<(unsigned)((n + 63) / 64), 128, 0, s>>>(soa, aos, stride, first, n);
 }
 
@@ -650,6 +868,7 @@ void launch_selftest_div(const LbmConst &C, unsigned long long seed, long long n
 #define LUMA_INST(L) \
 	template void launch_step<L>(const StepArgs &, bool, bool, int, cudaStream_t, int64_t *); \
 	template void launch_bc<L>(const StepArgs &, bool, bool, cudaStream_t, int64_t *); \
+	template void launch_velsrc<L>(const VelSrcArgs &, cudaStream_t, int64_t *); \
 	template void launch_cell_words<L>(const GeomArgs &, cudaStream_t); \
 	template void launch_synthetic<L>(const SynthArgs &, cudaStream_t); \
 	template void launch_aos_to_soa<L>(const double *, double *, long long, long long, long long, cudaStream_t); \

@@ -28,11 +28,37 @@ struct StepArgs
 	double hF[3];             // 0.5 * F
 	LbmConst C;
 	// boundary sites
-	const long long *bc_list; // local site ids of velocity/pressure sites
+	const long long *bc_list; // local site ids of the sites k_bc handles (classes 2, 3, 4), ascending
+	const int *bc_extra;      // per list entry: extra advances of the time averages (see tavg_update), or nullptr
 	int n_bc;
 	const double *uin;        // [3][M] ux_in, uy_in, uz_in
-	double ramp;              // getVelocityRampCoefficient((t+1)*dt)
+	double ramp;              // getVelocityRampCoefficient((t+1)*dt)   regularised BC, optimised.cpp:331
+	double ramp_t;            // getVelocityRampCoefficient(t*dt)       forced-equilibrium BC, optimised.cpp:258
 	double rho_out;
+	// per-link handling of class-4 sites (and of regularised sites when `general` is set)
+	const uint8_t *types;     // eType per cell
+	int general;              // the grid has eSlip / eExtrapolateRight / forced-equilibrium sources
+	int regularised;          // L_REGULARISED_BOUNDARIES
+	int velramp_on;           // L_VELOCITY_RAMP defined: forced-equilibrium sources take u = u_in[j]*ramp_t
+	// time-averaged statistics (L_COMPUTE_TIME_AVERAGED_QUANTITIES, optimised.cpp:895-917)
+	double *tav;              // SoA [1 + D + 3D-3][stride]: rho, u_p, u_p*u_q (p <= q) or nullptr
+	double t_now, t_next;     // (double)t and (double)(t + 1) of this step
+};
+
+// sites whose stored velocity the forced-equilibrium BC overwrites (optimised.cpp:259-263)
+struct VelSrcArgs
+{
+	const long long *list;    // local ids of the non-regularised eVelocity sites on owned planes
+	int n;
+	const uint8_t *types;
+	const uint32_t *bcdesc;   // wall descriptors (slip destinations)
+	double *u;
+	long long stride;
+	const double *uin;
+	double ramp_t;
+	int P, M, K, N;
+	int wrap_x;
+	int x_first;              // global x of local plane 0
 };
 
 struct GeomArgs
@@ -43,6 +69,7 @@ struct GeomArgs
 	int P, M, K;
 	int wrap_x;
 	int p_begin, p_end;       // planes that get a cell word (owned planes)
+	int regularised;
 };
 
 struct SynthArgs
@@ -69,12 +96,15 @@ struct SynthArgs
 
 template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches);
+template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
+void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);
 template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first_cell, long long ncells, cudaStream_t s);
 template <class L> void launch_soa_to_aos(const double *soa, double *aos, long long stride, long long first_cell, long long ncells, cudaStream_t s);
-void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int D, long long first_cell, long long ncells, cudaStream_t s);
-void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int D, long long first_cell, long long ncells, cudaStream_t s);
+// vectors of ncomp = 2, 3 or 6 components per site (u, ui_timeav, uiuj_timeav)
+void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int ncomp, long long first_cell, long long ncells, cudaStream_t s);
+void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int ncomp, long long first_cell, long long ncells, cudaStream_t s);
 void launch_types_from_i32(const int32_t *in, uint8_t *out, long long n, cudaStream_t s);
 void launch_types_to_i32(const uint8_t *in, int32_t *out, long long n, cudaStream_t s);
 void launch_selftest_div(const LbmConst &C, unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t s);

@@ -53,6 +53,19 @@ struct D2Q9
 
 template <class L> __host__ __device__ constexpr int opposite(int v) { return v == L::Q - 1 ? v : (v ^ 1); }
 
+// GridUtils::getReflect (src/GridUtils.cpp:46-51, :60-64, :495): the direction whose component
+// `plane` is negated and whose other components are those of v
+template <class L> __host__ __device__ constexpr int reflect(int v, int plane)
+{
+	for (int r = 0; r < L::Q; ++r)
+	{
+		bool same = true;
+		for (int e = 0; e < 3; ++e) same = same && (L::c(r, e) == ((e == plane) ? -L::c(v, e) : L::c(v, e)));
+		if (same) return r;
+	}
+	return v;
+}
+
 // ---- constants derived on the host exactly as the reference derives them ----
 struct LbmConst
 {
@@ -75,16 +88,21 @@ __device__ __forceinline__ double div_const(double a, double b, double y)
 }
 
 // ---- cell word (one uint32 per site, built once by build_cell_words) ----
-//  bits  0..18  link v bounces back: the site this population is pulled from is eSolid  (optimised.cpp:238)
-//  bits 19..20  class: 0 not updated (eSolid/eRefined), 1 eFluid, 2 eVelocity, 3 ePressure
-//  bit   21     site lies on the first/last row or column of the array (periodic wrap needed in y or z)
-//  bits 22..23  normalDirection          } regularised-BC descriptor of velocity/pressure sites,
+//  bits  0..17  link v (v < Q-1) bounces back: the site this population is pulled from is eSolid  (optimised.cpp:238)
+//  bit   18     site lies on the first/last row or column of the array (periodic wrap needed in y or z)
+//  bits 19..21  class: 0 not updated (eSolid, eRefined, non-regularised eVelocity), 1 eFluid with ordinary
+//               sources (the k_step fast path), 2 regularised eVelocity, 3 regularised ePressure, 4 general
+//               (eSlip, eExtrapolateRight, non-regularised ePressure, and eFluid sites that pull from an
+//               eExtrapolateRight / forced-equilibrium eVelocity source): handled per link from the eType array
+//  bits 22..23  normalDirection          } wall descriptor of velocity/pressure/slip sites,
 //  bits 24..29  normal vector + 1 (2b x3)} GridUtils::isWithinDomainWall, src/GridUtils.cpp:1369
 //  bits 30..31  edgeCount                }
-enum : uint32_t { CW_LINKS = 0x7FFFFu, CW_CLASS_SHIFT = 19, CW_EDGE = 1u << 21, CW_ND_SHIFT = 22, CW_N_SHIFT = 24, CW_EC_SHIFT = 30 };
-enum : uint32_t { CLS_SKIP = 0, CLS_FLUID = 1, CLS_VELOCITY = 2, CLS_PRESSURE = 3 };
+enum : uint32_t { CW_LINKS = 0x3FFFFu, CW_EDGE = 1u << 18, CW_CLASS_SHIFT = 19, CW_CLASS_MASK = 7u, CW_ND_SHIFT = 22, CW_N_SHIFT = 24, CW_EC_SHIFT = 30 };
+enum : uint32_t { CLS_SKIP = 0, CLS_FLUID = 1, CLS_VELOCITY = 2, CLS_PRESSURE = 3, CLS_GENERAL = 4 };
+// eType, inc/Enumerations.h:84-96
+enum : uint8_t { T_SOLID = 0, T_FLUID = 1, T_REFINED = 2, T_VELOCITY = 6, T_PRESSURE = 7, T_SLIP = 8, T_EXTRAPOLATE_RIGHT = 9 };
 
-__host__ __device__ inline uint32_t cw_class(uint32_t w) { return (w >> CW_CLASS_SHIFT) & 3u; }
+__host__ __device__ inline uint32_t cw_class(uint32_t w) { return (w >> CW_CLASS_SHIFT) & CW_CLASS_MASK; }
 __host__ __device__ inline uint32_t cw_pack_bc(int ec, int nd, int nx, int ny, int nz)
 {
 	return ((uint32_t)(ec & 3) << CW_EC_SHIFT) | ((uint32_t)(nd & 3) << CW_ND_SHIFT) |

@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 # eType, inc/Enumerations.h:84-96
-eSolid, eFluid, eRefined, eVelocity, ePressure = 0, 1, 2, 6, 7
+eSolid, eFluid, eRefined, eVelocity, ePressure, eSlip, eExtrapolateRight = 0, 1, 2, 6, 7, 8, 9
 # eCartesianDirection
 eXDirection, eYDirection, eZDirection = 0, 1, 2
 
@@ -70,6 +70,8 @@ class Definitions:
     L_VELOCITY_RAMP: Optional[float] = None
     L_REYNOLDS_RAMP: Optional[float] = None
     L_PRESSURE_DELTA: float = 0.0
+    # --- output options (definitions.h:130) ---
+    L_COMPUTE_TIME_AVERAGED_QUANTITIES: bool = False
     # --- bounce-back body given as an index box (stands in for input/geometry.config + point cloud) ---
     body_box: Optional[Tuple[int, int, int, int, int, int]] = None
 
@@ -194,10 +196,10 @@ class Definitions:
         return ec, nd, tuple(n)
 
     def boundary_site_descriptors(self, lattyp: np.ndarray, x_offset: int = 0):
-        """Descriptors for every eVelocity/ePressure site of a (slab of a) LatTyp array laid out
+        """Descriptors for every eVelocity/ePressure/eSlip site of a (slab of a) LatTyp array laid out
         k + K*(j + M*i): arrays (site, edge_count, normal_dir, normal[3])."""
         M, K = self.L_M, self.L_K
-        sites = np.flatnonzero((lattyp == eVelocity) | (lattyp == ePressure)).astype(np.int64)
+        sites = np.flatnonzero((lattyp == eVelocity) | (lattyp == ePressure) | (lattyp == eSlip)).astype(np.int64)
         x, y, z = self.positions()
         out = []
         for s in sites:

@@ -47,6 +47,7 @@ class GridObj:
         p.reynolds_ramp = defs.L_REYNOLDS_RAMP or 0.0
         p.re = float(defs.L_RE) if defs.L_RE is not None else 1.0
         p.t = t
+        p.time_averaged = int(defs.L_COMPUTE_TIME_AVERAGED_QUANTITIES)
         self.params = p
         self.rank, self.nranks = rank, nranks
         self.x_offset, self.x_count = p.x_offset, p.x_count
@@ -165,6 +166,18 @@ class GridObj:
         lt = np.empty(self.x_count * self.M_lim * self.K_lim, dtype=np.int32)
         capi.check(self._L.luma_b200_download_lattyp(self._h, 0, _ptr(lt)), self._h)
         return lt
+
+    def download_timeav(self):
+        """rho_timeav, ui_timeav, uiuj_timeav (inc/GridObj.h:93-95) of the owned planes."""
+        n = self.x_count * self.M_lim * self.K_lim
+        out = {"rho_timeav": np.empty(n), "ui_timeav": np.empty(n * self.D), "uiuj_timeav": np.empty(n * (3 * self.D - 3))}
+        capi.check(self._L.luma_b200_download_timeav(self._h, 0, _ptr(out["rho_timeav"]), _ptr(out["ui_timeav"]),
+                                                     _ptr(out["uiuj_timeav"])), self._h)
+        return out
+
+    def upload_timeav(self, rho_timeav=None, ui_timeav=None, uiuj_timeav=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (rho_timeav, ui_timeav, uiuj_timeav)]
+        capi.check(self._L.luma_b200_upload_timeav(self._h, 0, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2])), self._h)
 
     def computeLiftDrag(self):
         """Momentum-exchange force on bounce-back bodies of the last step (this rank's share)."""

@@ -8,7 +8,7 @@
  * in LUMA changes: inc/definitions.h still fixes the case at compile time, GridObj/GridManager/
  * ObjectManager build the grid, label walls and bodies, and the IO code reads the same host arrays.
  *
- *   first call : LumaCaseParams from the macros + members, wall descriptors of the velocity/pressure
+ *   first call : LumaCaseParams from the macros + members, wall descriptors of the velocity/pressure/slip
  *                sites from GridUtils::isWithinDomainWall, luma_b200_upload of f, rho, u, LatTyp.
  *   every call : luma_b200_step(1); GridObj::t, omega, nu follow the device.
  *   host sync  : rho, u (and f when a restart file is due) are downloaded into the GridObj arrays
@@ -110,6 +110,9 @@ void GridObj::LBM_multi_opt(int subcycle)
 #endif
 		p.re = static_cast<double>(L_RE);
 		p.t = t;
+#ifdef L_COMPUTE_TIME_AVERAGED_QUANTITIES
+		p.time_averaged = 1;
+#endif
 #if defined(L_USE_KBC_COLLISION) || defined(L_IBM_ON) || (L_NUM_LEVELS != 0)
 		L_ERROR("luma_b200: KBC, IBM and grid refinement are outside the accelerated path", GridUtils::logfile);
 #endif
@@ -129,7 +132,7 @@ void GridObj::LBM_multi_opt(int subcycle)
 		{
 			const int64_t id = k + (int64_t)j * K_lim + (int64_t)i * K_lim * M_lim;
 			const eType ty = LatTyp[id];
-			if (ty != eVelocity && ty != ePressure) continue;
+			if (ty != eVelocity && ty != ePressure && ty != eSlip) continue;
 			eCartesianDirection nd = eXDirection; unsigned int ec = 0;
 			nv[0] = nv[1] = nv[2] = 0;
 			LumaSiteBC s = { id, 0, 0, { 0, 0, 0 }, { 0, 0, 0 } };
@@ -147,6 +150,9 @@ void GridObj::LBM_multi_opt(int subcycle)
 	if (subcycle == LUMA_B200_SYNC_HOST)
 	{
 		check(luma_b200_download(g_dev, halo, LUMA_B200_F | LUMA_B200_RHO | LUMA_B200_U, &f[0], &rho[0], &u[0]), "download");
+#ifdef L_COMPUTE_TIME_AVERAGED_QUANTITIES
+		check(luma_b200_download_timeav(g_dev, halo, &rho_timeav[0], &ui_timeav[0], &uiuj_timeav[0]), "download_timeav");
+#endif
 		return;
 	}
 
@@ -164,6 +170,11 @@ void GridObj::LBM_multi_opt(int subcycle)
 	 * luma_b200_forces() in io_writeForcesOnObjects -- see INTEGRATION.md */
 #endif
 	if (what) check(luma_b200_download(g_dev, halo, what, &f[0], &rho[0], &u[0]), "download");
+#ifdef L_COMPUTE_TIME_AVERAGED_QUANTITIES
+	/* io_hdf5 / io_lite write the averages with the grid output (src/GridObj_ops_io.cpp:764-791, :1144-1262) */
+	if (t % L_GRID_OUT_FREQ == 0)
+		check(luma_b200_download_timeav(g_dev, halo, &rho_timeav[0], &ui_timeav[0], &uiuj_timeav[0]), "download_timeav");
+#endif
 
 	/* the reference's running average of the step time (optimised.cpp:172-183) */
 	const double secs = static_cast<double>(clock() - t_start) / CLOCKS_PER_SEC;

@@ -51,6 +51,12 @@ def main():
                     a = got[nm].reshape(-1, width)
                     b = getattr(ref, nm).reshape(-1, width)[sl]
                     assert np.array_equal(a, b), "rank %d %s %s t=%d %s: %s" % (rank, name, mode, s, nm, first_diff(a.ravel(), b.ravel()))
+                if case.time_averaged:
+                    tav = g.download_timeav()
+                    for nm, width in (("rho_timeav", 1), ("ui_timeav", D), ("uiuj_timeav", 3 * D - 3)):
+                        a = tav[nm].reshape(-1, width)
+                        b = getattr(ref, nm).reshape(-1, width)[sl]
+                        assert np.array_equal(a, b), "rank %d %s %s t=%d %s: %s" % (rank, name, mode, s, nm, first_diff(a.ravel(), b.ravel()))
             if case.ld_out:
                 F = torch.tensor(g.computeLiftDrag(), dtype=torch.float64, device="cuda")
                 dist.all_reduce(F)

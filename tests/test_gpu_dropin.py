@@ -22,7 +22,7 @@ def _digest(path):
     return hashlib.sha256(np.fromfile(path, dtype=np.float64).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("name", ["cav2d_64", "cyl3d", "chan3d", "tunnel2d", "cav2d_reramp"])
+@pytest.mark.parametrize("name", ["cav2d_64", "cyl3d", "chan3d", "tunnel2d", "cav2d_reramp", "sliptunnel2d", "fevel2d_tav", "pleft3d_tav"])
 def test_luma_host_with_gpu_time_step_reproduces_reference_digests(name):
     exe = os.path.join(REF, "luma_dropin_" + name)
     if not os.path.exists(exe):
@@ -35,7 +35,7 @@ def test_luma_host_with_gpu_time_step_reproduces_reference_digests(name):
         assert r.returncode == 0, r.stdout.decode()[-2000:] + open(os.path.join(out, "luma_ref_log.out")).read()[-2000:]
         for tag in ["init"] + ["t%d" % s for s in steps]:
             snap = gold["snapshots"][tag]
-            for nm in ("f", "rho", "u"):
+            for nm in ("f", "rho", "u") + (("rho_timeav", "ui_timeav", "uiuj_timeav") if case.time_averaged else ()):
                 assert _digest(os.path.join(out, "%s.%s.f64" % (tag, nm))) == snap[nm], (name, tag, nm)
             if tag != "init":
                 sc = dict(l.strip().split("=", 1) for l in open(os.path.join(out, tag + ".scalars.txt")) if "=" in l)

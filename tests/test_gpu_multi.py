@@ -16,7 +16,9 @@ def test_slabs_match_serial_oracle(world):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     # cases whose x extent leaves >= 4 planes per rank and whose BC extrapolation stays inside a slab
-    names = "chan3d,cyl3d,cav3d_32,chan2d,cyl2d" if world <= 4 else "chan3d,cyl3d,chan2d,cyl2d"
+    names = "chan3d,cyl3d,chan2d,cyl2d,slipchan3d,sliptunnel2d,sliptunnel3d,fevel2d,fevel3d,fevel2d_tav,tunnel2d_tav"
+    if world <= 4:
+        names += ",cav3d_32,cav3d_tav,felid3d"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29610 + world), os.path.join(HERE, "mgpu_worker.py"), names]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)

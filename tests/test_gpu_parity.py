@@ -33,11 +33,16 @@ def _golden(name):
         return json.load(fh)
 
 
-def _assert_same(name, tag, got, ref):
+def _assert_same(name, tag, got, ref, g=None):
     for nm in ("f", "rho", "u"):
         a, b = got[nm], getattr(ref, nm)
         assert max_rel_err(a, b) <= TOL, (name, tag, nm, first_diff(a, b))
         assert np.array_equal(a, b), "%s %s %s: %s" % (name, tag, nm, first_diff(a, b))
+    if g is not None and ref.case.time_averaged:
+        tav = g.download_timeav()
+        for nm in ("rho_timeav", "ui_timeav", "uiuj_timeav"):
+            a, b = tav[nm], getattr(ref, nm)
+            assert np.array_equal(a, b), "%s %s %s: %s" % (name, tag, nm, first_diff(a, b))
 
 
 def _steps(case, cap):
@@ -61,9 +66,13 @@ def test_upload_path_bitwise_vs_oracle(name):
         assert g.t == ref.t == s
         assert g.omega == ref.omega
         got = g.download()
-        _assert_same(name, "t%d" % s, got, ref)
+        _assert_same(name, "t%d" % s, got, ref, g)
         snap = gold["snapshots"]["t%d" % s]
         assert (snap["f"], snap["rho"], snap["u"]) == (_digest(got["f"]), _digest(got["rho"]), _digest(got["u"]))
+        if case.time_averaged:
+            tav = g.download_timeav()
+            for nm in ("rho_timeav", "ui_timeav", "uiuj_timeav"):
+                assert snap[nm] == _digest(tav[nm]), (name, s, nm)
     g.close(); ref.close()
 
 
@@ -79,8 +88,23 @@ def test_device_init_path_bitwise_vs_oracle(name):
     for s in _steps(case, 100):
         g.LBM_multi_opt(s - g.t)
         ref.step(s - ref.t)
-        _assert_same(name, "t%d" % s, g.download(), ref)
+        _assert_same(name, "t%d" % s, g.download(), ref, g)
     g.close(); ref.close()
+
+
+def test_time_averages_survive_a_host_round_trip():
+    """download_timeav -> new handle -> upload + upload_timeav (what a restart does) continues bit-identically"""
+    case = CASES["cyl2d_tav"]
+    ref = port.PortGrid(case)
+    a = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    a.LBM_multi_opt(13); ref.step(13)
+    st, tav = a.download(), a.download_timeav()
+    b = luma_b200.GridObj(defs_from_case(case), t=13)
+    b.upload(st["f"], st["rho"], st["u"], a.LatTyp, ref.uin(0), ref.uin(1), ref.uin(2))
+    b.upload_timeav(tav["rho_timeav"], tav["ui_timeav"], tav["uiuj_timeav"])
+    b.LBM_multi_opt(20); ref.step(20)
+    _assert_same("cyl2d_tav", "restart", b.download(), ref, b)
+    a.close(); b.close(); ref.close()
 
 
 def test_div_const_equals_ieee_division_on_device():
@@ -141,6 +165,24 @@ def test_unsupported_and_fatal_conditions_are_reported():
         g2.upload(ref.f, ref.rho, ref.u, lt)
     assert e.value.code == capi.EUNSUPPORTED
     g.close(); g2.close(); ref.close()
+    # a slip site outside every wall region (optimised.cpp:577) and an eExtrapolateRight site whose
+    # "two planes to the left" do not exist (optimised.cpp:249 would read off the array)
+    case = CASES["fevel2d"]
+    ref = port.PortGrid(case)
+    MK = case.M * case.K
+    g3 = luma_b200.GridObj(defs_from_case(case))
+    lt = ref.lattyp.copy(); lt[(case.N // 2) * MK + case.M // 2] = 8
+    with pytest.raises(capi.LumaB200Error) as e:
+        g3.upload(ref.f, ref.rho, ref.u, lt)
+    assert e.value.code == capi.EBC_NOT_WALL
+    lt = ref.lattyp.copy(); lt[1 * MK + case.M // 2] = 9
+    with pytest.raises(capi.LumaB200Error) as e:
+        g3.upload(ref.f, ref.rho, ref.u, lt)
+    assert e.value.code == capi.EBC_OFFGRID
+    with pytest.raises(capi.LumaB200Error) as e:
+        g3.download_timeav()
+    assert e.value.code == capi.ESTATE
+    g3.close(); ref.close()
 
 
 def test_full_size_c2_properties():

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(names) >= 18
     for nm in names:
         assert hasattr(L, nm), "symbol %s declared in include/luma_b200.h is not exported" % nm
-    assert L.luma_b200_abi_version() == 1
+    assert L.luma_b200_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
@@ -108,7 +108,7 @@ def test_definitions_derive_the_reference_scalars(name):
     lt = g.lattyp
     wall = g.wall.reshape(-1, 5)
     desc = d.boundary_site_descriptors(lt)
-    assert len(desc) == int(np.isin(lt, (6, 7)).sum())
+    assert len(desc) == int(np.isin(lt, (6, 7, 8)).sum())
     for site, ec, nd, n in desc[:: max(1, len(desc) // 500)]:
         assert (ec, nd, *n) == tuple(int(v) for v in wall[site]), (name, site)
     for s in (0, 1, 7, 100):

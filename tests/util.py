@@ -21,6 +21,7 @@ def defs_from_case(case: Case) -> Definitions:
         L_REGULARISED_BOUNDARIES=case.regularised,
         L_VELOCITY_RAMP=case.velocity_ramp, L_REYNOLDS_RAMP=case.reynolds_ramp,
         L_PRESSURE_DELTA=case.pressure_delta,
+        L_COMPUTE_TIME_AVERAGED_QUANTITIES=case.time_averaged,
         body_box=case.box,
     )
 
