@@ -191,6 +191,14 @@ int  luma_b200_step(luma_b200_t *h, int32_t nsteps);
 int  luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what,
                         double *f_aos, double *rho, double *u_aos);
 int  luma_b200_download_lattyp(luma_b200_t *h, int32_t halo, int32_t *lattyp);
+/* Asynchronous download for hosts that write output while the next steps run (the IO points of
+ * src/main_lbm.cpp:449-561 moved off the critical path): the fields are snapshotted on the device in the host
+ * layout, in stream order after the steps issued so far, and copied on a separate stream; the arrays
+ * (pinned host memory for a truly asynchronous copy) may be read after luma_b200_download_wait().  A second
+ * download_async before the wait queues behind the first. */
+int  luma_b200_download_async(luma_b200_t *h, int32_t halo, unsigned what,
+                              double *f_aos, double *rho, double *u_aos);
+int  luma_b200_download_wait(luma_b200_t *h);
 
 /* ---- time-averaged statistics (handles created with time_averaged = 1): rho_timeav [cells],
  *      ui_timeav [cells*D], uiuj_timeav [cells*(3D-3)], the reference's arrays (inc/GridObj.h:93-95,

@@ -38,6 +38,12 @@ class LumaSiteBC(C.Structure):
                 ("normal", C.c_int8 * 3), ("pad_", C.c_int8 * 3)]
 
 
+# the same 16-byte record as a numpy dtype (arrays of descriptors are handed over without a Python loop)
+import numpy as _np  # noqa: E402
+SITE_BC_DTYPE = _np.dtype({"names": ["site", "edge_count", "normal_dir", "normal"],
+                           "formats": ["<i8", "i1", "i1", ("i1", (3,))], "offsets": [0, 8, 9, 10], "itemsize": 16})
+
+
 class LumaSyntheticCase(C.Structure):
     _fields_ = [("wall_type", C.c_int32 * 6), ("wall_cells", C.c_int32 * 6), ("u_in", C.c_double * 3),
                 ("ux_in", C.POINTER(C.c_double)), ("uy_in", C.POINTER(C.c_double)), ("uz_in", C.POINTER(C.c_double)),
@@ -105,6 +111,8 @@ def load(build_if_missing: bool = True):
     L.luma_b200_step.argtypes = [H, C.c_int32]
     L.luma_b200_download.argtypes = [H, C.c_int32, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
     L.luma_b200_download_lattyp.argtypes = [H, C.c_int32, C.c_void_p]
+    L.luma_b200_download_async.argtypes = [H, C.c_int32, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.luma_b200_download_wait.argtypes = [H]
     L.luma_b200_download_timeav.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.luma_b200_upload_timeav.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.luma_b200_get_time.argtypes = [H, _ip, _dp, _dp]
@@ -115,7 +123,7 @@ def load(build_if_missing: bool = True):
     L.luma_b200_halo_plan.argtypes = [C.POINTER(LumaCaseParams), C.POINTER(LumaHaloMsg), C.c_int32, _ip]
     L.luma_b200_selftest_div_const.argtypes = [C.c_int32, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     for nm in ("create", "slab", "comm_unique_id", "comm_init", "upload", "init_synthetic", "step", "download",
-               "download_lattyp", "download_timeav", "upload_timeav", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
+               "download_lattyp", "download_async", "download_wait", "download_timeav", "upload_timeav", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
         getattr(L, "luma_b200_" + nm).restype = C.c_int
     if L.luma_b200_abi_version() != 2:
         raise ImportError("libluma_b200.so ABI version mismatch")

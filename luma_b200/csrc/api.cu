@@ -78,8 +78,11 @@ struct luma_b200
 	void *staging = nullptr;
 	size_t staging_bytes = 0;
 	double *momex_dev = nullptr;
-	cudaStream_t s_main = nullptr, s_comm = nullptr;
-	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	cudaStream_t s_main = nullptr, s_comm = nullptr, s_copy = nullptr;
+	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_snap = nullptr, ev_copied = nullptr;
+	double *snap = nullptr;         // snapshot of rho / u (AoS) / f (AoS) feeding an asynchronous download
+	size_t snap_bytes = 0;
+	bool copy_pending = false;
 	ncclComm_t comm = nullptr;
 	LbmConst C;
 	double omega = 0.0, nu = 0.0;
@@ -220,6 +223,10 @@ static void free_all(luma_b200_t *h)
 	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+	if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+	if (h->s_copy) cudaStreamDestroy(h->s_copy);
+	cudaFree(h->snap);
 	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_comm) cudaStreamDestroy(h->s_comm);
@@ -272,6 +279,9 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
 	CK(cudaEventCreate(&h->ev_t0));
 	CK(cudaEventCreate(&h->ev_t1));
+	CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
 	const size_t fbytes = (size_t)h->stride * h->Q * sizeof(double);
 	cudaError_t e = cudaMalloc(&h->f[0], fbytes);
 	if (e == cudaSuccess) e = cudaMalloc(&h->f[1], fbytes);
@@ -412,7 +422,11 @@ static inline int lat_c(int Q, int v, int d) { return (Q == 19) ? D3Q19::c(v, d)
 
 // after h->types (owned planes) and h->bcdesc exist on the device: ghost planes, validation of the
 // boundary sites the way the reference would L_ERROR on them, the list of sites k_bc handles, cell words.
-static int finalize_geometry(luma_b200_t *h)
+// `desc_of(id, plane, j, k)` gives the packed wall descriptor of an OWNED site (the dense device array
+// h->bcdesc holds the same values; the host does not download it).
+extern "C++" {
+template <class DescFn>
+static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 {
 	const LumaCaseParams &p = h->p;
 	if (h->ghost)
@@ -421,10 +435,8 @@ static int finalize_geometry(luma_b200_t *h)
 		int rc = exchange_ghost_planes(h, h->s_main);
 		if (rc) return rc;
 	}
-	std::vector<uint8_t> types((size_t)h->cells);
-	std::vector<uint32_t> desc((size_t)h->cells);
+	std::vector<uint8_t> types((size_t)h->cells + 8, 0);
 	CK(cudaMemcpyAsync(types.data(), h->types, (size_t)h->cells, cudaMemcpyDeviceToHost, h->s_main));
-	CK(cudaMemcpyAsync(desc.data(), h->bcdesc, (size_t)h->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
 
 	const int P = h->P, M = p.M, K = p.K, Q = h->Q, D = h->D;
@@ -446,6 +458,13 @@ static int finalize_geometry(luma_b200_t *h)
 		for (int j = 0; j < M; ++j)
 			for (int k = 0; k < K; ++k)
 			{
+				if (K - k >= 8)
+				{
+					// eight sites at a time: nothing to do where all of them are eSolid (0) or eFluid (1)
+					uint64_t w8;
+					memcpy(&w8, row + (size_t)j * K + k, 8);
+					if ((w8 & 0xFEFEFEFEFEFEFEFEull) == 0) { k += 7; continue; }
+				}
 				const uint8_t t = row[(size_t)j * K + k];
 				if (t == T_SOLID || t == T_FLUID) continue;
 				const long long id = site(pl, j, k);
@@ -478,7 +497,7 @@ static int finalize_geometry(luma_b200_t *h)
 				if (t == T_SLIP)
 				{
 					general = true;
-					if ((desc[(size_t)id] >> CW_EC_SHIFT) == 0)
+					if ((desc_of(id, pl, j, k) >> CW_EC_SHIFT) == 0)
 						FAIL(LUMA_B200_EBC_NOT_WALL, "Slip wall not located inside a domain wall region. Not currently supported.");   // optimised.cpp:577
 					list.push_back(id);
 					continue;
@@ -493,7 +512,7 @@ static int finalize_geometry(luma_b200_t *h)
 				}
 
 				// regularised velocity / pressure site (optimised.cpp:313-510)
-				const uint32_t d = desc[(size_t)id];
+				const uint32_t d = desc_of(id, pl, j, k);
 				const int ec = (int)(d >> CW_EC_SHIFT);
 				if (ec == 0) FAIL(LUMA_B200_EBC_NOT_WALL, luma_b200_strerror(LUMA_B200_EBC_NOT_WALL));
 				if (ec > 1 && t == T_PRESSURE) FAIL(LUMA_B200_EBC_PRESSURE_EDGE, luma_b200_strerror(LUMA_B200_EBC_PRESSURE_EDGE));
@@ -583,6 +602,7 @@ static int finalize_geometry(luma_b200_t *h)
 	CK(e1); CK(e2);
 	return LUMA_B200_OK;
 }
+}  // extern "C++"
 
 int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const double *rho, const double *u_aos,
 	const int32_t *lattyp, const LumaSiteBC *bc_sites, size_t n_bc,
@@ -636,8 +656,11 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	if (uz_in) memcpy(&uin[2 * (size_t)p.M], uz_in, sizeof(double) * p.M);
 	CK(cudaMemcpyAsync(h->uin, uin.data(), uin.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
 
-	// wall descriptors of the boundary sites
-	std::vector<uint32_t> desc((size_t)h->cells, 0u);
+	// wall descriptors of the boundary sites: sparse on the host, scattered into the dense device array
+	std::vector<long long> dsite;
+	std::vector<uint32_t> dval;
+	dsite.reserve(n_bc); dval.reserve(n_bc);
+	bool sorted = true;
 	for (size_t b = 0; b < n_bc; ++b)
 	{
 		const LumaSiteBC &s = bc_sites[b];
@@ -645,13 +668,41 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 		const long long loc = s.site - host_off;
 		if (loc < 0 || loc >= owned) continue;     // descriptor of a halo site: not ours
 		if (s.edge_count < 0 || s.edge_count > 3 || s.normal_dir < 0 || s.normal_dir > 2) FAIL(LUMA_B200_EINVAL, "upload: bc descriptor");
-		desc[(size_t)(loc + dev_off)] = s.edge_count ? cw_pack_bc(s.edge_count, s.normal_dir, s.normal[0], s.normal[1], s.normal[2]) : 0u;
+		if (!s.edge_count) continue;
+		if (!dsite.empty() && loc + dev_off <= dsite.back()) sorted = false;
+		dsite.push_back(loc + dev_off);
+		dval.push_back(cw_pack_bc(s.edge_count, s.normal_dir, s.normal[0], s.normal[1], s.normal[2]));
 	}
-	CK(cudaMemcpyAsync(h->bcdesc, desc.data(), desc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_main));
+	if (!sorted)
+	{
+		std::vector<size_t> order(dsite.size());
+		for (size_t a = 0; a < order.size(); ++a) order[a] = a;
+		std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return dsite[x] < dsite[y]; });
+		std::vector<long long> s2(dsite.size()); std::vector<uint32_t> v2(dsite.size());
+		for (size_t a = 0; a < order.size(); ++a) { s2[a] = dsite[order[a]]; v2[a] = dval[order[a]]; }
+		dsite.swap(s2); dval.swap(v2);      // a site given twice keeps its last descriptor on the device (scatter order) and its first here
+	}
+	CK(cudaMemsetAsync(h->bcdesc, 0, (size_t)h->cells * sizeof(uint32_t), h->s_main));
+	if (!dsite.empty())
+	{
+		const size_t need = dsite.size() * (sizeof(long long) + sizeof(uint32_t));
+		rc = ensure_staging(h, need);
+		if (rc) return rc;
+		long long *ids_dev = (long long *)h->staging;
+		uint32_t *val_dev = (uint32_t *)(ids_dev + dsite.size());
+		CK(cudaMemcpyAsync(ids_dev, dsite.data(), dsite.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s_main));
+		CK(cudaMemcpyAsync(val_dev, dval.data(), dval.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_main));
+		launch_scatter_u32(h->bcdesc, ids_dev, val_dev, (int)dsite.size(), h->s_main);
+		h->st.kernel_launches++;
+	}
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(h->s_main));
 
-	rc = finalize_geometry(h);
+	rc = finalize_geometry(h, [&](long long id, int, int, int) -> uint32_t
+	{
+		const auto it = std::lower_bound(dsite.begin(), dsite.end(), id);
+		return (it != dsite.end() && *it == id) ? dval[(size_t)(it - dsite.begin())] : 0u;
+	});
 	if (rc) return rc;
 	if (h->ghost)
 	{
@@ -697,7 +748,23 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	h->st.kernel_launches++;
 	CK(cudaGetLastError());
 	h->cur = 0;
-	int rc = finalize_geometry(h);
+	// the descriptor k_synthetic stores for a site, restated in cell indices (GridUtils::isWithinDomainWall)
+	const int ghost = h->ghost, x_off = p.x_offset;
+	int rc = finalize_geometry(h, [&, c](long long, int pl, int j, int k) -> uint32_t
+	{
+		const int gi = x_off + (pl - ghost);
+		int ec = 0, nd = 0, n0 = 0, n1 = 0, n2 = 0;
+		if (gi < c->wall_cells[0]) { nd = 0; n0 = 1; ++ec; }
+		if (gi >= p.N - c->wall_cells[1]) { nd = 0; n0 = -1; ++ec; }
+		if (j < c->wall_cells[2]) { nd = 1; n1 = 1; ++ec; }
+		if (j >= p.M - c->wall_cells[3]) { nd = 1; n1 = -1; ++ec; }
+		if (p.dims == 3)
+		{
+			if (k < c->wall_cells[4]) { nd = 2; n2 = 1; ++ec; }
+			if (k >= p.K - c->wall_cells[5]) { nd = 2; n2 = -1; ++ec; }
+		}
+		return (ec > 0) ? cw_pack_bc(ec, nd, n0, n1, n2) : 0u;
+	});
 	if (rc) return rc;
 	h->t = p.t; h->omega = p.omega;
 	h->have_state = true; h->stepped = false;
@@ -874,6 +941,67 @@ int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_ao
 	return LUMA_B200_OK;
 }
 
+// Asynchronous variant for hosts that write their output while the next steps run: the requested fields
+// are snapshotted on the device in the host layout (stream-ordered after the steps so far, a few hundred
+// microseconds), then copied to the host on a separate stream while luma_b200_step keeps the GPU busy.
+int luma_b200_download_async(luma_b200_t *h, int32_t halo, unsigned what, double *f_aos, double *rho, double *u_aos)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "download before upload/init_synthetic");
+	if (halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "download: halo");
+	if (((what & LUMA_B200_F) && !f_aos) || ((what & LUMA_B200_RHO) && !rho) || ((what & LUMA_B200_U) && !u_aos))
+		FAIL(LUMA_B200_EINVAL, "download: null array");
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const long long owned = (long long)p.x_count * h->MK;
+	const long long host_off = (long long)halo * h->MK, dev_off = (long long)h->ghost * h->MK;
+	size_t need = 0;
+	if (what & LUMA_B200_RHO) need += (size_t)owned;
+	if (what & LUMA_B200_U) need += (size_t)owned * h->D;
+	if (what & LUMA_B200_F) need += (size_t)owned * h->Q;
+	need *= sizeof(double);
+	if (h->copy_pending) CK(cudaStreamWaitEvent(h->s_main, h->ev_copied, 0));      // the previous copy still reads the snapshot
+	if (h->snap_bytes < need)
+	{
+		if (h->copy_pending) CK(cudaEventSynchronize(h->ev_copied));
+		cudaFree(h->snap); h->snap = nullptr; h->snap_bytes = 0;
+		if (cudaMalloc(&h->snap, need) != cudaSuccess) { cudaGetLastError(); FAIL(LUMA_B200_ENOMEM, "snapshot buffer"); }
+		h->snap_bytes = need;
+	}
+	double *s_rho = h->snap, *s_u = s_rho + ((what & LUMA_B200_RHO) ? owned : 0), *s_f = s_u + ((what & LUMA_B200_U) ? owned * h->D : 0);
+	if (what & LUMA_B200_RHO)
+		CK(cudaMemcpyAsync(s_rho, h->rho + dev_off, (size_t)owned * sizeof(double), cudaMemcpyDeviceToDevice, h->s_main));
+	if (what & LUMA_B200_U)
+	{
+		launch_u_soa_to_aos(h->u, s_u, h->stride, h->D, dev_off, owned, h->s_main);
+		h->st.kernel_launches++;
+	}
+	if (what & LUMA_B200_F)
+	{
+		if (h->Q == 19) launch_soa_to_aos<D3Q19>(h->f[h->cur], s_f, h->stride, dev_off, owned, h->s_main);
+		else launch_soa_to_aos<D2Q9>(h->f[h->cur], s_f, h->stride, dev_off, owned, h->s_main);
+		h->st.kernel_launches++;
+	}
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(h->ev_snap, h->s_main));
+	CK(cudaStreamWaitEvent(h->s_copy, h->ev_snap, 0));
+	if (what & LUMA_B200_RHO) CK(cudaMemcpyAsync(rho + host_off, s_rho, (size_t)owned * sizeof(double), cudaMemcpyDeviceToHost, h->s_copy));
+	if (what & LUMA_B200_U) CK(cudaMemcpyAsync(u_aos + host_off * h->D, s_u, (size_t)owned * h->D * sizeof(double), cudaMemcpyDeviceToHost, h->s_copy));
+	if (what & LUMA_B200_F) CK(cudaMemcpyAsync(f_aos + host_off * h->Q, s_f, (size_t)owned * h->Q * sizeof(double), cudaMemcpyDeviceToHost, h->s_copy));
+	CK(cudaEventRecord(h->ev_copied, h->s_copy));
+	h->copy_pending = true;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_download_wait(luma_b200_t *h)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	CK(cudaSetDevice(h->p.device));
+	if (h->copy_pending) CK(cudaEventSynchronize(h->ev_copied));
+	h->copy_pending = false;
+	return LUMA_B200_OK;
+}
+
 // rho_timeav [cells], ui_timeav [cells*D], uiuj_timeav [cells*(3D-3)] in the reference's AoS layout (inc/GridObj.h:93-95)
 static int transfer_timeav(luma_b200_t *h, int32_t halo, double *rho_tav, double *ui_tav, double *uiuj_tav, bool to_host)
 {
@@ -1021,6 +1149,8 @@ int luma_b200_sync(luma_b200_t *h)
 	CK(cudaSetDevice(h->p.device));
 	CK(cudaStreamSynchronize(h->s_main));
 	CK(cudaStreamSynchronize(h->s_comm));
+	CK(cudaStreamSynchronize(h->s_copy));
+	h->copy_pending = false;
 	return LUMA_B200_OK;
 }
 

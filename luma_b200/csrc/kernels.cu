@@ -532,6 +532,16 @@ void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_
 	if (n > 0) k_force_general<<<(n + 127) / 128, 128, 0, s>>>(cw, ids, n);
 }
 
+__global__ void k_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n) out[ids[t]] = vals[t];
+}
+void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s)
+{
+	if (n > 0) k_scatter_u32<<<(n + 127) / 128, 128, 0, s>>>(out, ids, vals, n);
+}
+
 #define LUMA_DISPATCH(KERNEL, GRID, THREADS) \
 	do { \
 		const int key = (smag ? 4 : 0) | (force ? 2 : 0) | (a.tav ? 1 : 0); \

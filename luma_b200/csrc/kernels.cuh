@@ -98,6 +98,7 @@ template <class L> void launch_step(const StepArgs &a, bool smag, bool force, in
 template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches);
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
 void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_t s);
+void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);
 template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first_cell, long long ncells, cudaStream_t s);

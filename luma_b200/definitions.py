@@ -195,16 +195,33 @@ class Definitions:
                 nd, n[2], ec = 2, -1, ec + 1
         return ec, nd, tuple(n)
 
-    def boundary_site_descriptors(self, lattyp: np.ndarray, x_offset: int = 0):
+    def boundary_site_descriptors(self, lattyp: np.ndarray, x_offset: int = 0) -> np.ndarray:
         """Descriptors for every eVelocity/ePressure/eSlip site of a (slab of a) LatTyp array laid out
-        k + K*(j + M*i): arrays (site, edge_count, normal_dir, normal[3])."""
+        k + K*(j + M*i), as GridUtils::isWithinDomainWall gives them: a record array with the layout of
+        LumaSiteBC (site, edge_count, normal_dir, normal[3]); iterating it yields those four per site."""
+        from .capi import SITE_BC_DTYPE
         M, K = self.L_M, self.L_K
+        lattyp = np.asarray(lattyp).ravel()
         sites = np.flatnonzero((lattyp == eVelocity) | (lattyp == ePressure) | (lattyp == eSlip)).astype(np.int64)
         x, y, z = self.positions()
-        out = []
-        for s in sites:
-            i, rem = divmod(int(s), M * K)
-            j, k = divmod(rem, K)
-            ec, nd, n = self._wall(x[(i + x_offset) % self.L_N], y[j], z[k] if self.L_DIMS == 3 else 0.0)
-            out.append((int(s), ec, nd if ec else 0, n))
+        i, rem = np.divmod(sites, M * K)
+        j, k = np.divmod(rem, K)
+        px, py = x[(i + x_offset) % self.L_N], y[j]
+        pz = z[k] if self.L_DIMS == 3 else np.zeros(sites.size)
+        th = self.wall_thickness
+        dh = self.dh
+        Lx, Ly, Lz = dh * self.L_N, dh * self.L_M, dh * self.L_K
+        n = np.zeros((sites.size, 3), dtype=np.int8)
+        nd = np.zeros(sites.size, dtype=np.int8)
+        ec = np.zeros(sites.size, dtype=np.int8)
+        tests = [(0, 1, (px > 0.0) & (px < th[0])), (0, -1, (px < Lx) & (px > Lx - th[1])),
+                 (1, 1, (py > 0.0) & (py < th[2])), (1, -1, (py < Ly) & (py > Ly - th[3]))]
+        if self.L_DIMS == 3:
+            tests += [(2, 1, (pz > 0.0) & (pz < th[4])), (2, -1, (pz < Lz) & (pz > Lz - th[5]))]
+        for d, sign, hit in tests:            # same order as the reference: the last wall hit names normal_dir
+            n[hit, d] = sign
+            nd[hit] = d
+            ec[hit] += 1
+        out = np.zeros(sites.size, dtype=SITE_BC_DTYPE)
+        out["site"], out["edge_count"], out["normal_dir"], out["normal"] = sites, ec, nd, n
         return out

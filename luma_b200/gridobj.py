@@ -102,10 +102,13 @@ class GridObj:
             raise ValueError("upload: array sizes do not match the local grid")
         if bc_sites is None:
             bc_sites = self.defs.boundary_site_descriptors(lt, x_offset=self.x_offset - halo)
-        arr = (capi.LumaSiteBC * max(len(bc_sites), 1))()
-        for n, (site, ec, nd, nv) in enumerate(bc_sites):
-            arr[n].site, arr[n].edge_count, arr[n].normal_dir = site, ec, nd
-            arr[n].normal[0], arr[n].normal[1], arr[n].normal[2] = nv
+        if not (isinstance(bc_sites, np.ndarray) and bc_sites.dtype == capi.SITE_BC_DTYPE):
+            rec = np.zeros(len(bc_sites), dtype=capi.SITE_BC_DTYPE)
+            for n, (site, ec, nd, nv) in enumerate(bc_sites):
+                rec[n] = (site, ec, nd, nv)
+            bc_sites = rec
+        bc_sites = np.ascontiguousarray(bc_sites)
+        arr = bc_sites.ctypes.data_as(C.POINTER(capi.LumaSiteBC)) if len(bc_sites) else None
         prof = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (ux_in, uy_in, uz_in)]
         capi.check(self._L.luma_b200_upload(self._h, halo, _ptr(f), _ptr(rho), _ptr(u), _ptr(lt), arr, len(bc_sites),
                                             _ptr(prof[0]), _ptr(prof[1]), _ptr(prof[2])), self._h)
@@ -148,6 +151,16 @@ class GridObj:
             u = np.empty(n * self.D)
         capi.check(self._L.luma_b200_download(self._h, 0, what, _ptr(f), _ptr(rho), _ptr(u)), self._h)
         return {"f": f, "rho": rho, "u": u}
+
+    def download_async(self, what, out):
+        """Start a download of this step's fields into the (pinned) arrays of `out` while later steps run;
+        read them after download_wait().  src/main_lbm.cpp:449-561 with the IO off the critical path."""
+        capi.check(self._L.luma_b200_download_async(self._h, 0, what, _ptr(out.get("f")) if what & capi.F else None,
+                                                    _ptr(out.get("rho")) if what & capi.RHO else None,
+                                                    _ptr(out.get("u")) if what & capi.U else None), self._h)
+
+    def download_wait(self):
+        capi.check(self._L.luma_b200_download_wait(self._h), self._h)
 
     @property
     def f(self):

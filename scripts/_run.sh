@@ -1,4 +1,4 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/s3_tests2.log
-timeout 300 python scripts/quick_perf.py > gpurun_out/s3_quick2.log 2>&1
-cat gpurun_out/s3_tests2.log gpurun_out/s3_quick2.log
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s3_tests4.log
+timeout 300 python bench.py > gpurun_out/s3_bench2_n1.json 2> gpurun_out/s3_bench2_n1.err
+cat gpurun_out/s3_tests4.log gpurun_out/s3_bench2_n1.json; tail -3 gpurun_out/s3_bench2_n1.err

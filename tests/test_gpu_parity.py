@@ -107,6 +107,30 @@ def test_time_averages_survive_a_host_round_trip():
     a.close(); b.close(); ref.close()
 
 
+def test_async_download_is_a_snapshot():
+    """download_async returns the fields of the step it was issued after, even though more steps run
+    (and overwrite rho,u of the boundary sites) before the copy is waited for"""
+    case = CASES["cyl3d"]
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    n = case.N * case.M * case.K
+    g.LBM_multi_opt(10)
+    want = g.download()
+    out = {"f": np.empty(n * case.Q), "rho": np.empty(n), "u": np.empty(n * case.dims)}
+    g.download_async(capi.F | capi.RHO | capi.U, out)
+    g.LBM_multi_opt(7)
+    out2 = {"rho": np.empty(n), "u": np.empty(n * case.dims)}
+    g.download_async(capi.RHO | capi.U, out2)          # queues behind the first
+    g.LBM_multi_opt(3)
+    g.download_wait()
+    for nm in ("f", "rho", "u"):
+        assert np.array_equal(out[nm], want[nm]), nm
+    ref = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    ref.LBM_multi_opt(17)
+    w2 = ref.download(capi.RHO | capi.U)
+    assert np.array_equal(out2["rho"], w2["rho"]) and np.array_equal(out2["u"], w2["u"])
+    g.close(); ref.close()
+
+
 def test_div_const_equals_ieee_division_on_device():
     """2 x 2^31 random operands on the GPU: the 3-operation constant division must equal `/` bit for bit
     (the proof by enumeration is tests/test_constdiv_exact.py)."""
