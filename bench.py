@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- MLUPS of LUMA's level-0 time step (GridObj::LBM_multi_opt) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -9,7 +9,8 @@ One JSON line on rank 0.  A "step" is one LBM time step of the whole level-0 gri
 
 * workload c2 (default): BASELINE.json configs[1], 3-D lid-driven cavity D3Q19 BGK Re=1000, 256^3 cells
   per GPU (at N GPUs the cavity is N*256 x 256 x 256, x-slab per GPU -> weak scaling);
-  workload c5: configs[4], 384^3 cells per GPU.
+  workload c5: configs[4], 384^3 cells per GPU; c3 / c4: configs[2] / configs[3] at their fixed global size
+  (512^3 periodic channel with Guo forcing; 1024x256x256 inlet/outlet + Smagorinsky + cylinder).
 * value  : global cells * K / device time of the K steps (CUDA events on the library's stream,
            max over ranks), state resident in HBM.
 * e2e    : the same K steps through the reference-facing API with HOST buffers: upload of the host
@@ -47,8 +48,32 @@ BYTES_PER_LUP = 304.0          # 19 populations x 8 B read + 19 x 8 B written (t
 OUT_FREQ = 100                 # L_GRID_OUT_FREQ used by the e2e leg
 
 
+WEAK = ("c2", "c5")            # cells per GPU fixed; c3 / c4 have a fixed global grid (strong scaling)
+
+
 def workload_defs(name: str, ngpus: int):
+    """SURVEY.md 8(d) table of synthetic inputs, as definitions.h macros."""
     import luma_b200
+    if name == "c3":
+        # configs[2]: periodic channel 512^3, bounce-back walls in y, Guo forcing along x; nu_lbm = 0.05
+        # (omega 1.538), gravity such that the Poiseuille maximum is u_lbm ~ 0.05
+        res = 512
+        return luma_b200.Definitions(
+            L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_BX=1.0, L_BY=1.0, L_BZ=1.0,
+            L_RE=None, L_NU=1.0 / res, L_NO_FLOW=True,
+            L_WALL_LEFT=luma_b200.eFluid, L_WALL_RIGHT=luma_b200.eFluid, L_WALL_FRONT=luma_b200.eFluid,
+            L_WALL_BACK=luma_b200.eFluid, L_WALL_THICKNESS_CELLS=(0, 0, 1, 1, 0, 0),
+            L_GRAVITY_ON=True, L_GRAVITY_FORCE=0.0158, L_GRAVITY_DIRECTION=0)
+    if name == "c4":
+        # configs[3]: 1024x256x256, velocity inlet / pressure outlet (regularised), Smagorinsky LES, velocity
+        # ramp, square cylinder 32x32 spanning z at x ~ 256; omega 1.98
+        res = 256
+        return luma_b200.Definitions(
+            L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_BX=4.0, L_BY=1.0, L_BZ=1.0,
+            L_RE=7600.0, L_NO_FLOW=True, L_USE_BGKSMAG=True, L_CSMAG=0.3, L_VELOCITY_RAMP=0.5,
+            L_WALL_LEFT=luma_b200.eVelocity, L_WALL_RIGHT=luma_b200.ePressure, L_WALL_FRONT=luma_b200.eFluid,
+            L_WALL_BACK=luma_b200.eFluid, L_WALL_THICKNESS_CELLS=(1, 1, 1, 1, 0, 0),
+            body_box=(256, 288, 112, 144, 0, 256))
     res = {"c2": 256, "c5": 384}[name]
     return luma_b200.Definitions(
         L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_BX=float(ngpus), L_BY=1.0, L_BZ=1.0,
@@ -56,6 +81,11 @@ def workload_defs(name: str, ngpus: int):
 
 
 def workload_name(name: str, ngpus: int) -> str:
+    if name == "c3":
+        return "BASELINE configs[2]: 3D periodic channel D3Q19, bounce-back walls, Guo forcing, 512x512x512 cells over %d x-slab(s)" % ngpus
+    if name == "c4":
+        return ("BASELINE configs[3]: flow past a square cylinder D3Q19, velocity inlet / pressure outlet, Smagorinsky LES, "
+                "1024x256x256 cells over %d x-slab(s)" % ngpus)
     res = {"c2": 256, "c5": 384}[name]
     base = {"c2": "BASELINE configs[1]: 3D lid-driven cavity D3Q19 BGK Re=1000",
             "c5": "BASELINE configs[4]: weak-scaling cavity D3Q19 BGK"}[name]
@@ -302,11 +332,14 @@ def main_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if args.workload in WEAK else "strong",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, world), "cells_per_gpu": cells_local,
                        "omega": g.omega, "parallelism": "x-slab x%d, NCCL p2p halo of the 5 outgoing populations per face" % world,
                        "l2": "inputs larger than L2 (2 lattices x %.2f GB per GPU)" % (cells_local * 19 * 8 / 1e9),
+                       "kernel_variant": "k_step<D3Q19,%s,%s>" % ("Smagorinsky" if defs.L_USE_BGKSMAG else "BGK",
+                                                                   "Guo force" if defs.L_GRAVITY_ON else "no force"),
                        "arithmetic": "bit-identical to the reference CPU build (tests/test_gpu_parity.py)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "pct_hbm_roofline": 100.0 * value * BYTES_PER_LUP / 1e3 / (world * peak),
@@ -325,7 +358,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["c2", "c5"], default="c2")
+    ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5"], default="c2")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

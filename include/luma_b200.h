@@ -131,6 +131,7 @@ typedef struct LumaStats {
 	int64_t step_kernel_launches;
 	double  step_kernel_ms;     /* summed device time of those launches */
 	int64_t step_kernel_cells;  /* summed lattice updates covered by those launches */
+	int64_t graph_launches;     /* CUDA-graph replays (batches of steps of launch-bound grids) since create */
 } LumaStats;
 
 #define LUMA_B200_F   1u

@@ -54,7 +54,8 @@ class LumaStats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("ms_last_call", C.c_double), ("ms_per_step", C.c_double),
                 ("mlups_last_call", C.c_double), ("kernel_launches", C.c_int64),
                 ("halo_bytes_per_step", C.c_int64), ("cells", C.c_int64),
-                ("step_kernel_launches", C.c_int64), ("step_kernel_ms", C.c_double), ("step_kernel_cells", C.c_int64)]
+                ("step_kernel_launches", C.c_int64), ("step_kernel_ms", C.c_double), ("step_kernel_cells", C.c_int64),
+                ("graph_launches", C.c_int64)]
 
 
 class LumaHaloMsg(C.Structure):

@@ -55,6 +55,15 @@ struct NcclApi
 };
 static NcclApi g_nccl;
 
+struct GraphSlot
+{
+	cudaGraphExec_t exec = nullptr;
+	double omega = 0.0;
+	int n_bc = -1;
+	int epoch = -1;
+	int64_t nodes = 0;
+};
+
 struct luma_b200
 {
 	LumaCaseParams p;
@@ -79,7 +88,7 @@ struct luma_b200
 	size_t staging_bytes = 0;
 	double *momex_dev = nullptr;
 	cudaStream_t s_main = nullptr, s_comm = nullptr, s_copy = nullptr;
-	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_snap = nullptr, ev_copied = nullptr;
+	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_snap = nullptr, ev_copied = nullptr, ev_fork = nullptr;
 	double *snap = nullptr;         // snapshot of rho / u (AoS) / f (AoS) feeding an asynchronous download
 	size_t snap_bytes = 0;
 	bool copy_pending = false;
@@ -91,6 +100,9 @@ struct luma_b200
 	bool stepped = false;
 	LumaStats st;
 	std::string err;
+	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
+	int graph_steps = 0;            // 0 = never use graphs
+	int geometry_epoch = 0;         // bumped by upload / init_synthetic
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
 	size_t prof_used = 0;
@@ -224,10 +236,12 @@ static void free_all(luma_b200_t *h)
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
 	if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
 	if (h->ev_copied) cudaEventDestroy(h->ev_copied);
 	if (h->s_copy) cudaStreamDestroy(h->s_copy);
 	cudaFree(h->snap);
 	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+	for (GraphSlot &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_comm) cudaStreamDestroy(h->s_comm);
 }
@@ -262,6 +276,15 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	memset(&h->st, 0, sizeof(h->st));
 	h->st.cells = (long long)p->x_count * h->MK;
 	make_constants(h->C, h->Q);
+	{
+		// CUDA-graph batches: by default for grids small enough to be launch-bound; LUMA_B200_GRAPH_STEPS=0 turns
+		// them off, LUMA_B200_GRAPH_CELLS moves the size limit
+		const char *gsv = getenv("LUMA_B200_GRAPH_STEPS"), *gcv = getenv("LUMA_B200_GRAPH_CELLS");
+		const long long limit = (gcv && *gcv) ? atoll(gcv) : (4LL << 20);
+		int gsteps = (gsv && *gsv) ? atoi(gsv) : 16;
+		if (gsteps < 2 || h->cells > limit) gsteps = 0;
+		h->graph_steps = gsteps & ~1;
+	}
 	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 
 	int ndev = 0;
@@ -281,6 +304,7 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	CK(cudaEventCreate(&h->ev_t1));
 	CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
 	CK(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
 	const size_t fbytes = (size_t)h->stride * h->Q * sizeof(double);
 	cudaError_t e = cudaMalloc(&h->f[0], fbytes);
@@ -712,6 +736,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	}
 	h->t = p.t; h->omega = p.omega;
 	h->have_state = true; h->stepped = false;
+	++h->geometry_epoch;
 	return LUMA_B200_OK;
 }
 
@@ -768,6 +793,7 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	if (rc) return rc;
 	h->t = p.t; h->omega = p.omega;
 	h->have_state = true; h->stepped = false;
+	++h->geometry_epoch;
 	return LUMA_B200_OK;
 }
 
@@ -834,38 +860,129 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		x.t_now = (double)t_now; x.t_next = (double)(t_now + 1);
 	};
 
+	// one time step enqueued on the handle's streams (also the body of the captured CUDA graph below)
+	auto enqueue_step = [&](StepArgs &x) -> int
+	{
+	// The list kernel (boundary / class-4 sites) and the fluid kernel read the same lattice and write disjoint
+	// sites, so they run side by side: k_bc goes to the high-priority stream, where its latency-bound threads
+	// fill in behind the bandwidth-bound k_step instead of holding the GPU alone at the start of every step.
+	// (with per-kernel profiling events on, k_bc runs first on the main stream so that the events time k_step alone)
+	const bool side = h->n_bc > 0 && !h->profiling;
+	if (!h->ghost)
+	{
+		x.p0 = 0; x.pstep = 1;
+		if (!side)
+		{
+			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_main, &h->st.kernel_launches);
+			else launch_bc<D2Q9>(x, smag, force, h->s_main, &h->st.kernel_launches);
+		}
+		if (side)
+		{
+			CK(cudaEventRecord(h->ev_fork, h->s_main));
+			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
+			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_comm, &h->st.kernel_launches);
+			else launch_bc<D2Q9>(x, smag, force, h->s_comm, &h->st.kernel_launches);
+			CK(cudaEventRecord(h->ev_comm, h->s_comm));
+		}
+		if (h->Q == 19) main_kernel<D3Q19>(h, x, smag, force, h->P);
+		else main_kernel<D2Q9>(h, x, smag, force, h->P);
+		if (side) CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
+	}
+	else
+	{
+		// slab faces first, then their populations go out on the comm stream while the interior
+		// planes are computed (no overlap exists in the reference: MpiManager.cpp:631 runs after :159)
+		CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
+		StepArgs e = x;
+		e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
+		const int nedge = (owned > 1) ? 2 : 1;
+		StepArgs in = x;
+		in.p0 = 2; in.pstep = 1;
+		if (!side)
+		{
+			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_main, &h->st.kernel_launches);
+			else launch_bc<D2Q9>(x, smag, force, h->s_main, &h->st.kernel_launches);
+		}
+		if (side)
+		{
+			CK(cudaEventRecord(h->ev_fork, h->s_main));
+			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
+			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_comm, &h->st.kernel_launches);
+			else launch_bc<D2Q9>(x, smag, force, h->s_comm, &h->st.kernel_launches);
+		}
+		if (h->Q == 19) launch_step<D3Q19>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches);
+		else launch_step<D2Q9>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches);
+		CK(cudaEventRecord(h->ev_edge, h->s_main));
+		CK(cudaStreamWaitEvent(h->s_comm, h->ev_edge, 0));
+		int rc = exchange_populations(h, h->f[h->cur ^ 1], h->s_comm);
+		if (rc) return rc;
+		CK(cudaEventRecord(h->ev_comm, h->s_comm));
+		if (h->Q == 19) main_kernel<D3Q19>(h, in, smag, force, owned - 2);
+		else main_kernel<D2Q9>(h, in, smag, force, owned - 2);
+	}
+		return LUMA_B200_OK;
+	};
+
+	// Launch-bound grids (BASELINE configs[0], 256^2: ~3 us of work per step): batches of `graph_steps` steps are
+	// captured once into a CUDA graph -- same kernels, same arguments, the two streams become graph branches -- and
+	// replayed with one launch each.  Only while every per-step scalar is constant (ramps finished, no time
+	// averages, no profiling events), on a single rank, and never for the last step of a call (which stores rho,u).
+	const int GS = h->graph_steps;
+	auto graph_ready = [&](int t_now) -> bool
+	{
+		if (GS < 2 || h->ghost || h->profiling || h->tav) return false;
+		if (velocity_ramp_coef(p, t_now * p.dt) != 1.0 || velocity_ramp_coef(p, (t_now + 1) * p.dt) != 1.0) return false;
+		if (p.reynolds_ramp_on && !((t_now + 1) * p.dt > p.reynolds_ramp)) return false;
+		return true;
+	};
+
 	int s = 0;
 	while (s < nsteps)
 	{
+		if (nsteps - s - 1 >= GS && graph_ready(h->t))
+		{
+			StepArgs b = a;
+			step_scalars(b, h->t);
+			GraphSlot &gs = h->graphs[h->cur];
+			if (gs.exec && (gs.omega != b.omega || gs.n_bc != h->n_bc || gs.epoch != h->geometry_epoch))
+			{
+				cudaGraphExecDestroy(gs.exec); gs.exec = nullptr;
+			}
+			if (!gs.exec)
+			{
+				const int64_t before = h->st.kernel_launches;
+				cudaGraph_t graph = nullptr;
+				CK(cudaStreamBeginCapture(h->s_main, cudaStreamCaptureModeRelaxed));
+				int rc = LUMA_B200_OK;
+				for (int i = 0; i < GS && rc == LUMA_B200_OK; ++i)
+				{
+					b.fin = h->f[h->cur ^ (i & 1)]; b.fout = h->f[h->cur ^ (i & 1) ^ 1];
+					b.write_macro = 0;
+					rc = enqueue_step(b);
+				}
+				const cudaError_t ce = cudaStreamEndCapture(h->s_main, &graph);
+				gs.nodes = h->st.kernel_launches - before;
+				h->st.kernel_launches = before;
+				if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+				CK(ce);
+				const cudaError_t ie = cudaGraphInstantiate(&gs.exec, graph, 0);
+				cudaGraphDestroy(graph);
+				CK(ie);
+				gs.omega = b.omega; gs.n_bc = h->n_bc; gs.epoch = h->geometry_epoch;
+			}
+			CK(cudaGraphLaunch(gs.exec, h->s_main));
+			h->st.kernel_launches += gs.nodes;
+			h->st.graph_launches++;
+			h->t += GS;       // GS is even: h->cur is unchanged
+			s += GS;
+			continue;
+		}
 		step_scalars(a, h->t);
 		a.fin = h->f[h->cur]; a.fout = h->f[h->cur ^ 1];
 		a.write_macro = (s == nsteps - 1) ? 1 : 0;
-
-		if (!h->ghost)
 		{
-			a.p0 = 0; a.pstep = 1;
-			if (h->Q == 19) { launch_bc<D3Q19>(a, smag, force, h->s_main, &h->st.kernel_launches); main_kernel<D3Q19>(h, a, smag, force, h->P); }
-			else { launch_bc<D2Q9>(a, smag, force, h->s_main, &h->st.kernel_launches); main_kernel<D2Q9>(h, a, smag, force, h->P); }
-		}
-		else
-		{
-			// slab faces first, then their populations go out on the comm stream while the interior
-			// planes are computed (no overlap exists in the reference: MpiManager.cpp:631 runs after :159)
-			CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
-			StepArgs e = a;
-			e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
-			const int nedge = (owned > 1) ? 2 : 1;
-			StepArgs in = a;
-			in.p0 = 2; in.pstep = 1;
-			if (h->Q == 19) { launch_bc<D3Q19>(a, smag, force, h->s_main, &h->st.kernel_launches); launch_step<D3Q19>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches); }
-			else { launch_bc<D2Q9>(a, smag, force, h->s_main, &h->st.kernel_launches); launch_step<D2Q9>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches); }
-			CK(cudaEventRecord(h->ev_edge, h->s_main));
-			CK(cudaStreamWaitEvent(h->s_comm, h->ev_edge, 0));
-			int rc = exchange_populations(h, h->f[h->cur ^ 1], h->s_comm);
+			const int rc = enqueue_step(a);
 			if (rc) return rc;
-			CK(cudaEventRecord(h->ev_comm, h->s_comm));
-			if (h->Q == 19) main_kernel<D3Q19>(h, in, smag, force, owned - 2);
-			else main_kernel<D2Q9>(h, in, smag, force, owned - 2);
 		}
 		if (a.write_macro && h->n_vel)
 		{

@@ -20,7 +20,7 @@ namespace luma {
 #define LUMA_MIN_BLOCKS 6
 #endif
 #ifndef LUMA_MIN_BLOCKS_SMAG
-#define LUMA_MIN_BLOCKS_SMAG 4  /* the Smagorinsky variants need ~120 registers */
+#define LUMA_MIN_BLOCKS_SMAG 5  /* measured on B200: 5 x 128 threads (<= 102 registers, no spills) beats 4 and 3; 6 spills */
 #endif
 #ifndef LUMA_LOAD_MODE
 #define LUMA_LOAD_MODE 0      /* 0 ld.global.nc (__ldg), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate, 3 plain */

@@ -19,10 +19,44 @@ from oracle.cases import CASES  # noqa: E402
 from util import defs_from_case, first_diff  # noqa: E402
 
 
+def fullsize(rank, world, local, workload, steps):
+    """order-independent checksums of f, rho, u of a full-size bench workload after `steps` steps"""
+    import bench
+    defs = bench.workload_defs(workload, world)
+    uid = ring.broadcast_unique_id(dist, rank) if world > 1 else None
+    g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid).LBM_initGrid()
+    g.LBM_multi_opt(steps)
+    got = g.download()
+    acc = []
+    for nm in ("f", "rho", "u"):
+        bits = got[nm].view(np.uint64)
+        acc += [int(np.add.reduce(bits, dtype=np.uint64)), int(np.bitwise_xor.reduce(bits))]
+    F = g.computeLiftDrag()
+    g.close()
+    if world > 1:
+        t = torch.tensor([[a & 0xFFFFFFFF, a >> 32] for a in acc], dtype=torch.int64, device="cuda")
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        tot = [0] * len(acc)
+        for p in parts:
+            for i, (lo, hi) in enumerate(p.cpu().tolist()):
+                v = lo | (hi << 32)
+                tot[i] = (tot[i] + v) & 0xFFFFFFFFFFFFFFFF if i % 2 == 0 else tot[i] ^ v
+        acc = tot
+    if rank == 0:
+        print("fullsize checksums %s on %d GPU(s): %s" % (workload, world, " ".join("%016x" % a for a in acc)), flush=True)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if sys.argv[1].startswith("fullsize:"):
+        _, workload, steps = sys.argv[1].split(":")
+        fullsize(rank, world, local, workload, int(steps))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     names = sys.argv[1].split(",")
     for name in names:
         case = CASES[name]

@@ -25,3 +25,24 @@ def test_slabs_match_serial_oracle(world):
     out = r.stdout.decode()
     assert r.returncode == 0, out[-4000:]
     assert out.count("mgpu ok") == len(names.split(",")), out[-4000:]
+
+
+@pytest.mark.parametrize("workload,steps", [("c4", 20), ("c3", 12)])
+def test_full_size_slabs_equal_one_gpu(workload, steps):
+    """BASELINE configs[2] / configs[3] at full size: the x-slab run on all GPUs of the box must leave the same bits
+    as the single-GPU run (compared through order-independent 64-bit wrap-sums and xors of f, rho, u)."""
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sums = {}
+    for n in (1, world):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+               "--master-addr", "127.0.0.1", "--master-port", str(29640 + n), os.path.join(HERE, "mgpu_worker.py"),
+               "fullsize:%s:%d" % (workload, steps)]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500)
+        out = r.stdout.decode()
+        assert r.returncode == 0, out[-4000:]
+        line = [l for l in out.splitlines() if l.startswith("fullsize checksums")]
+        assert len(line) == 1, out[-4000:]
+        sums[n] = line[0].split(":", 1)[1].strip()
+    assert sums[1] == sums[world], sums

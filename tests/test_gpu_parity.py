@@ -107,6 +107,28 @@ def test_time_averages_survive_a_host_round_trip():
     a.close(); b.close(); ref.close()
 
 
+@pytest.mark.parametrize("name,steps", [("cav2d_c1", 200), ("cav2d_64", 400), ("cav2d_reramp", 100), ("chan3d", 150)])
+def test_cuda_graph_batches_are_bitwise_and_used(name, steps):
+    """launch-bound grids replay captured batches of 16 steps (luma_b200_step); they start only once the
+    velocity / Reynolds ramps have ended and never cover the last step of a call"""
+    case = CASES[name]
+    ref = port.PortGrid(case)
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    g.LBM_multi_opt(steps); ref.step(steps)
+    _assert_same(name, "t%d" % steps, g.download(), ref)
+    g.LBM_multi_opt(37); ref.step(37)                      # odd count: the second call starts on the other lattice
+    _assert_same(name, "t%d" % (steps + 37), g.download(), ref)
+    assert g.omega == ref.omega and g.t == ref.t
+    n = g.stats()["graph_launches"]
+    ramp_end = 0
+    if case.velocity_ramp is not None:
+        ramp_end = int(case.velocity_ramp / case.dt) + 1
+    if case.reynolds_ramp is not None:
+        ramp_end = max(ramp_end, int(case.reynolds_ramp / case.dt) + 1)
+    assert n >= (steps - ramp_end - 1) // 16 - 1 and n >= 1, (n, ramp_end)
+    g.close(); ref.close()
+
+
 def test_async_download_is_a_snapshot():
     """download_async returns the fields of the step it was issued after, even though more steps run
     (and overwrite rho,u of the boundary sites) before the copy is waited for"""
