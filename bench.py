@@ -37,10 +37,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout at
-# NCCL_DEBUG=VERSION) would be a second one
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line.  Native libraries write there too (NCCL prints its "NCCL version ..."
+# banner on stdout), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the
+# saved descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 METRIC = "MLUPS (D3Q19 fp64)"
 UNIT = "MLUPS"
@@ -198,7 +204,7 @@ def main_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -344,7 +350,7 @@ def main_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "pct_hbm_roofline": 100.0 * value * BYTES_PER_LUP / 1e3 / (world * peak),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     g.close()
     if dist is not None:
         dist.barrier()
