@@ -86,3 +86,28 @@ def test_full_size_c4_cylinder_z_invariance_and_determinism():
     assert np.array_equal(again["rho"], out["rho"]) and np.array_equal(again["u"], out["u"])
     assert np.array_equal(h.computeLiftDrag(), F)
     h.close()
+
+
+def test_beyond_int32_element_offsets():
+    """640^3 cells: 4.98e9 population elements per lattice -- element offsets exceed 2^32, which the reference's
+    `int` indexing cannot address.  Same invariance / mass properties as the 512^3 channel."""
+    if _free_gb() < 110:
+        pytest.skip("needs ~95 GB of device memory")
+    res = 640
+    d = luma_b200.Definitions(
+        L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=None, L_NU=1.0 / res, L_NO_FLOW=True,
+        L_WALL_LEFT=luma_b200.eFluid, L_WALL_RIGHT=luma_b200.eFluid, L_WALL_FRONT=luma_b200.eFluid,
+        L_WALL_BACK=luma_b200.eFluid, L_WALL_THICKNESS_CELLS=(0, 0, 1, 1, 0, 0),
+        L_GRAVITY_ON=True, L_GRAVITY_FORCE=0.0158, L_GRAVITY_DIRECTION=0)
+    assert d.L_N * d.L_M * d.L_K * 19 > 2 ** 32
+    g = luma_b200.GridObj(d).LBM_initGrid()
+    g.LBM_multi_opt(12)
+    rho = g.download(capi.RHO)["rho"].reshape(res, res, res)
+    assert np.array_equal(rho, np.broadcast_to(rho[:1, :, :1], rho.shape))
+    line = rho[0, 1:-1, 0]
+    assert abs(float(line.sum(dtype=np.longdouble)) - (res - 2)) <= 1e-12 * res
+    del rho
+    ux = g.download(capi.U)["u"].reshape(res, res, res, 3)[..., 0]
+    assert np.array_equal(ux, np.broadcast_to(ux[:1, :, :1], ux.shape))
+    assert (ux[0, 1:-1, 0] > 0).all()
+    g.close()
