@@ -57,6 +57,9 @@ OUT_FREQ = 100                 # L_GRID_OUT_FREQ used by the e2e leg
 WEAK = ("c2", "c5")            # cells per GPU fixed; c3 / c4 have a fixed global grid (strong scaling)
 
 
+RES_OVERRIDE = None            # --res: cells per GPU edge of the cavity workloads (studies only; the default is the named size)
+
+
 def workload_defs(name: str, ngpus: int):
     """SURVEY.md 8(d) table of synthetic inputs, as definitions.h macros."""
     import luma_b200
@@ -80,7 +83,7 @@ def workload_defs(name: str, ngpus: int):
             L_WALL_LEFT=luma_b200.eVelocity, L_WALL_RIGHT=luma_b200.ePressure, L_WALL_FRONT=luma_b200.eFluid,
             L_WALL_BACK=luma_b200.eFluid, L_WALL_THICKNESS_CELLS=(1, 1, 1, 1, 0, 0),
             body_box=(256, 288, 112, 144, 0, 256))
-    res = {"c2": 256, "c5": 384}[name]
+    res = RES_OVERRIDE or {"c2": 256, "c5": 384}[name]
     return luma_b200.Definitions(
         L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_BX=float(ngpus), L_BY=1.0, L_BZ=1.0,
         L_RE=1000.0, L_UX0=1.0, L_WALL_TOP=luma_b200.eVelocity, L_REGULARISED_BOUNDARIES=True, L_NO_FLOW=True)
@@ -92,7 +95,7 @@ def workload_name(name: str, ngpus: int) -> str:
     if name == "c4":
         return ("BASELINE configs[3]: flow past a square cylinder D3Q19, velocity inlet / pressure outlet, Smagorinsky LES, "
                 "1024x256x256 cells over %d x-slab(s)" % ngpus)
-    res = {"c2": 256, "c5": 384}[name]
+    res = RES_OVERRIDE or {"c2": 256, "c5": 384}[name]
     base = {"c2": "BASELINE configs[1]: 3D lid-driven cavity D3Q19 BGK Re=1000",
             "c5": "BASELINE configs[4]: weak-scaling cavity D3Q19 BGK"}[name]
     return "%s, %dx%dx%d cells (%d^3 per GPU, x-slabs)" % (base, res * ngpus, res, res, res)
@@ -249,6 +252,13 @@ def main_ours(args):
 
     defs = workload_defs(args.workload, world)
     g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
+    halo = "none (single GPU)"
+    if world > 1:
+        halo = "NCCL send/recv of the 5 outgoing populations per face"
+        if args.halo == "p2p":
+            from luma_b200 import ring
+            ring.attach_p2p(dist, g, rank, world)
+            halo = "device-initiated: the 5 outgoing populations per face stored into the neighbour's ghost plane over NVLink (CUDA IPC), arrival flags"
     g.LBM_initGrid()
     cells_local = g.x_count * g.M_lim * g.K_lim
     cells_global = defs.L_N * defs.L_M * defs.L_K
@@ -342,7 +352,7 @@ def main_ours(args):
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, world), "cells_per_gpu": cells_local,
-                       "omega": g.omega, "parallelism": "x-slab x%d, NCCL p2p halo of the 5 outgoing populations per face" % world,
+                       "omega": g.omega, "parallelism": "x-slab x%d; halo exchange: %s" % (world, halo),
                        "l2": "inputs larger than L2 (2 lattices x %.2f GB per GPU)" % (cells_local * 19 * 8 / 1e9),
                        "kernel_variant": "k_step<D3Q19,%s,%s>" % ("Smagorinsky" if defs.L_USE_BGKSMAG else "BGK",
                                                                    "Guo force" if defs.L_GRAVITY_ON else "no force"),
@@ -365,7 +375,10 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5"], default="c2")
+    ap.add_argument("--halo", choices=["p2p", "nccl"], default="p2p", help="multi-GPU halo exchange: peer stores (default) or NCCL send/recv")
+    ap.add_argument("--res", type=int, default=None, help="cavity edge per GPU for c2/c5 (scaling studies; not the named config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    RES_OVERRIDE = a.res
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -154,6 +154,16 @@ int  luma_b200_slab(int32_t N, int32_t nranks, int32_t rank, int32_t *x_offset, 
 int  luma_b200_comm_unique_id(void *unique_id_128);
 int  luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128);
 
+/* Device-initiated exchange (optional, after luma_b200_comm_init and before upload/init): the ranks publish IPC
+ * handles of their lattices, the host hands every rank the blobs of its left (rank-1) and right (rank+1) ring
+ * neighbours (MPI_Allgather / torch.distributed.all_gather), and from then on luma_b200_step stores the outgoing
+ * populations straight into the neighbour GPU's ghost planes over NVLink and signals arrival with a flag -- no
+ * communication-library call per step.  Needs peer access between neighbouring GPUs (NVSwitch: always); without
+ * attach the NCCL send/recv path below runs.  Results are identical either way. */
+#define LUMA_B200_P2P_BLOB_BYTES 256
+int  luma_b200_p2p_export(luma_b200_t *h, void *blob_256);
+int  luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob_256, const void *right_blob_256);
+
 /* The per-step exchange of this rank, in issue order (one NCCL group): only the populations that
  * cross a slab face travel -- c_x = +1 to the +x neighbour (D3Q19 v = 0,6,8,14,17; D2Q9 0,4,6) from
  * the last owned plane into the neighbour's low ghost plane, c_x = -1 (1,7,9,15,16; 1,5,7) from the

@@ -55,6 +55,25 @@ struct NcclApi
 };
 static NcclApi g_nccl;
 
+// what a rank publishes so that its ring neighbours can store into its ghost planes (luma_b200_p2p_export)
+struct P2PBlob
+{
+	uint32_t magic;
+	int32_t rank, device, P;
+	long long stride, MK;
+	cudaIpcMemHandle_t f[2], flags;
+};
+static_assert(sizeof(P2PBlob) <= LUMA_B200_P2P_BLOB_BYTES, "P2P blob fits its ABI size");
+
+struct PeerMap
+{
+	void *base[3] = { nullptr, nullptr, nullptr };   // mapped f[0], f[1], flags of the neighbour (owned by this map)
+	double *f[2] = { nullptr, nullptr };
+	unsigned long long *flags = nullptr;
+	long long stride = 0;
+	int P = 0;
+};
+
 struct GraphSlot
 {
 	cudaGraphExec_t exec = nullptr;
@@ -100,6 +119,12 @@ struct luma_b200
 	bool stepped = false;
 	LumaStats st;
 	std::string err;
+	// device-initiated halo exchange (NVLink peer stores); falls back to NCCL send/recv when not attached
+	unsigned long long *flags = nullptr;   // [0] exchange number that arrived from the left neighbour, [1] from the right; +4: counter
+	int *halo_timeout = nullptr;           // set by k_halo_wait when a neighbour never showed up
+	PeerMap peer[2];                       // 0 = left (rank-1), 1 = right (rank+1); peer[1] aliases peer[0] when nranks == 2
+	bool p2p = false;
+	unsigned long long xchg = 0;           // exchanges published so far
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
 	int geometry_epoch = 0;         // bumped by upload / init_synthetic
@@ -242,6 +267,9 @@ static void free_all(luma_b200_t *h)
 	cudaFree(h->snap);
 	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
 	for (GraphSlot &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+	for (int side = 0; side < 2; ++side)
+		for (void *&b : h->peer[side].base) { if (b) cudaIpcCloseMemHandle(b); b = nullptr; }
+	cudaFree(h->flags); cudaFree(h->halo_timeout);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_comm) cudaStreamDestroy(h->s_comm);
 }
@@ -316,6 +344,8 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	if (e == cudaSuccess) e = cudaMalloc(&h->u, (size_t)h->stride * h->D * sizeof(double));
 	if (e == cudaSuccess) e = cudaMalloc(&h->uin, (size_t)3 * p->M * sizeof(double));
 	if (e == cudaSuccess) e = cudaMalloc(&h->momex_dev, (size_t)3 * 4096 * sizeof(double));
+	if (e == cudaSuccess && h->ghost) e = cudaMalloc(&h->flags, 64);
+	if (e == cudaSuccess && h->ghost) e = cudaMalloc(&h->halo_timeout, sizeof(int));
 	const size_t tav_bytes = (size_t)h->stride * (1 + h->D + 3 * h->D - 3) * sizeof(double);
 	if (e == cudaSuccess && p->time_averaged) e = cudaMalloc(&h->tav, tav_bytes);
 	if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return LUMA_B200_ENOMEM; }
@@ -323,6 +353,8 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	CK(cudaMemsetAsync(h->bcdesc, 0, (size_t)h->cells * sizeof(uint32_t), h->s_main));
 	CK(cudaMemsetAsync(h->uin, 0, (size_t)3 * p->M * sizeof(double), h->s_main));
 	if (h->tav) CK(cudaMemsetAsync(h->tav, 0, tav_bytes, h->s_main));      // init_grids.cpp:304-306
+	if (h->flags) CK(cudaMemsetAsync(h->flags, 0, 64, h->s_main));
+	if (h->halo_timeout) CK(cudaMemsetAsync(h->halo_timeout, 0, sizeof(int), h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
 	return LUMA_B200_OK;
 }
@@ -357,6 +389,62 @@ int luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128)
 	ncclUniqueId id;
 	memcpy(&id, unique_id_128, 128);
 	NK(g_nccl.CommInitRank(&h->comm, h->p.nranks, id, h->p.rank));
+	return LUMA_B200_OK;
+}
+
+int luma_b200_p2p_export(luma_b200_t *h, void *blob)
+{
+	if (!h || !blob) return LUMA_B200_EINVAL;
+	if (!h->ghost) FAIL(LUMA_B200_ESTATE, "p2p_export on a single-rank handle");
+	CK(cudaSetDevice(h->p.device));
+	P2PBlob b;
+	memset(&b, 0, sizeof(b));
+	b.magic = 0x4C423230u; b.rank = h->p.rank; b.device = h->p.device; b.P = h->P;
+	b.stride = h->stride; b.MK = h->MK;
+	CK(cudaIpcGetMemHandle(&b.f[0], h->f[0]));
+	CK(cudaIpcGetMemHandle(&b.f[1], h->f[1]));
+	CK(cudaIpcGetMemHandle(&b.flags, h->flags));
+	memset(blob, 0, LUMA_B200_P2P_BLOB_BYTES);
+	memcpy(blob, &b, sizeof(b));
+	return LUMA_B200_OK;
+}
+
+int luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob, const void *right_blob)
+{
+	if (!h || !left_blob || !right_blob) return LUMA_B200_EINVAL;
+	if (!h->ghost) FAIL(LUMA_B200_ESTATE, "p2p_attach on a single-rank handle");
+	if (h->p2p) FAIL(LUMA_B200_ESTATE, "p2p_attach called twice");
+	CK(cudaSetDevice(h->p.device));
+	const int n = h->p.nranks, want[2] = { (h->p.rank - 1 + n) % n, (h->p.rank + 1) % n };
+	const void *blobs[2] = { left_blob, right_blob };
+	for (int side = 0; side < 2; ++side)
+	{
+		P2PBlob b;
+		memcpy(&b, blobs[side], sizeof(b));
+		if (b.magic != 0x4C423230u || b.rank != want[side] || b.MK != h->MK)
+			FAIL(LUMA_B200_EINVAL, "p2p_attach: blob does not come from the ring neighbour");
+		PeerMap &pm = h->peer[side];
+		pm.stride = b.stride; pm.P = b.P;
+		if (side == 1 && n == 2)
+		{
+			// both neighbours are the same GPU: one mapping (an allocation can be opened once per process)
+			pm.f[0] = h->peer[0].f[0]; pm.f[1] = h->peer[0].f[1]; pm.flags = h->peer[0].flags;
+			continue;
+		}
+		const cudaIpcMemHandle_t *hd[3] = { &b.f[0], &b.f[1], &b.flags };
+		for (int k = 0; k < 3; ++k)
+		{
+			const cudaError_t e = cudaIpcOpenMemHandle(&pm.base[k], *hd[k], cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess)
+			{
+				cudaGetLastError();
+				h->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) + " (no peer access between the two GPUs? use the NCCL exchange)";
+				return LUMA_B200_ECUDA;
+			}
+		}
+		pm.f[0] = (double *)pm.base[0]; pm.f[1] = (double *)pm.base[1]; pm.flags = (unsigned long long *)pm.base[2];
+	}
+	h->p2p = true;
 	return LUMA_B200_OK;
 }
 
@@ -398,8 +486,41 @@ static int build_halo_plan(const LumaCaseParams &p, std::vector<LumaHaloMsg> &pl
 	return (int)plan.size();
 }
 
+// the same plan executed by this GPU alone: every send becomes stores into the receiver's ghost plane
+// (lattice index `li` on both sides: the ranks step in lockstep), receives become a wait on the arrival flags
+static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s)
+{
+	std::vector<LumaHaloMsg> plan;
+	build_halo_plan(h->p, plan);
+	HaloPushArgs a;
+	memset(&a, 0, sizeof(a));
+	for (const LumaHaloMsg &m : plan)
+	{
+		if (!m.is_send) continue;
+		// c_x = +1 populations go to the right neighbour's low ghost plane (0), c_x = -1 populations to the left
+		// neighbour's high ghost plane (P_left - 1); with two ranks both neighbours are the same GPU
+		const bool to_right = ((h->Q == 19) ? D3Q19::c(m.pop, 0) : D2Q9::c(m.pop, 0)) > 0;
+		const PeerMap &pm = h->peer[to_right ? 1 : 0];
+		const int dst_plane = to_right ? 0 : pm.P - 1;
+		a.src[a.nmsg] = h->f[li] + (long long)m.pop * h->stride + (long long)m.plane * h->MK;
+		a.dst[a.nmsg] = pm.f[li] + (long long)m.pop * pm.stride + (long long)dst_plane * h->MK;
+		++a.nmsg;
+	}
+	a.count = h->MK;
+	a.peer_flag[0] = h->peer[0].flags + 1;      // we are the left neighbour's RIGHT neighbour
+	a.peer_flag[1] = h->peer[1].flags + 0;      // and the right neighbour's LEFT neighbour
+	a.value = ++h->xchg;
+	a.done = reinterpret_cast<unsigned int *>(h->flags + 4);
+	launch_halo_push(a, s);
+	launch_halo_wait(h->flags, a.value, h->halo_timeout, s);
+	h->st.kernel_launches += 2;
+	CK(cudaGetLastError());
+	return LUMA_B200_OK;
+}
+
 static int exchange_populations(luma_b200_t *h, double *lat, cudaStream_t s)
 {
+	if (h->p2p && (lat == h->f[0] || lat == h->f[1])) return exchange_populations_p2p(h, lat == h->f[0] ? 0 : 1, s);
 	std::vector<LumaHaloMsg> plan;
 	build_halo_plan(h->p, plan);
 	const size_t cnt = (size_t)h->MK;
@@ -1002,6 +1123,12 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	CK(cudaEventRecord(h->ev_t1, h->s_main));
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(h->s_main));
+	if (h->p2p)
+	{
+		int timed_out = 0;
+		CK(cudaMemcpy(&timed_out, h->halo_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+		if (timed_out) FAIL(LUMA_B200_ENCCL, "halo exchange: a ring neighbour did not deliver its populations within 20 s");
+	}
 	float ms = 0.f;
 	CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
 	for (size_t e = 0; e + 1 < h->prof_used; e += 2)

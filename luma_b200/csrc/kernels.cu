@@ -576,6 +576,66 @@ template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cuda
 }
 
 // ------------------------------------------------------------------------------------------------
+// Halo exchange without a communication library: the populations that leave through a slab face are
+// stored straight into the neighbour GPU's ghost plane (NVLink peer memory, mapped through CUDA IPC);
+// the last CTA to finish publishes the exchange number in the neighbours' arrival flags
+// (fence.sys + release store), and the receiver's k_halo_wait acquires it before anything reads the
+// ghost planes.  Replaces MpiManager::mpi_communicate's pack / MPI_Isend / MPI_Recv / unpack
+// (src/MpiManager.cpp:631-815) by one store per population element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_halo_push(const HaloPushArgs a)
+{
+	const int m = blockIdx.y;
+	const double *__restrict__ src = a.src[m];
+	double *__restrict__ dst = a.dst[m];
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += (long long)gridDim.x * blockDim.x)
+		dst[i] = src[i];
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		const unsigned int total = gridDim.x * gridDim.y;
+		if (atomicAdd(a.done, 1u) == total - 1)
+		{
+			*a.done = 0;
+			__threadfence_system();
+			for (int side = 0; side < 2; ++side)
+				asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a.peer_flag[side]), "l"(a.value) : "memory");
+		}
+	}
+}
+
+void launch_halo_push(const HaloPushArgs &a, cudaStream_t s)
+{
+	if (a.nmsg <= 0) return;
+	unsigned bx = (unsigned)((a.count + 255) / 256);
+	if (bx > 64) bx = 64;
+	k_halo_push<<<dim3(bx, (unsigned)a.nmsg), 256, 0, s>>>(a);
+}
+
+// thread 0 waits for the left neighbour's data, thread 1 for the right neighbour's; gives up after
+// 20 s (a dead peer must not hang the GPU) and reports it through *timed_out
+__global__ void k_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out)
+{
+	if (threadIdx.x > 1) return;
+	unsigned long long t0, t1, seen;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for (;;)
+	{
+		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + threadIdx.x) : "memory");
+		if (seen >= value) break;
+		__nanosleep(64);
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if (t1 - t0 > 20000000000ull) { *timed_out = 1; break; }
+	}
+}
+
+void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s)
+{
+	k_halo_wait<<<1, 32, 0, s>>>(flags, value, timed_out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // geometry: cell words from the eType array (+ host- or device-made wall descriptors)
 // ------------------------------------------------------------------------------------------------
 template <class L>

@@ -61,6 +61,18 @@ struct VelSrcArgs
 	int x_first;              // global x of local plane 0
 };
 
+// ---- device-initiated halo exchange over NVLink peer memory (kernels.cu k_halo_push / k_halo_wait) ----
+struct HaloPushArgs
+{
+	const double *src[10];    // local: one population plane of the lattice just written (M*K doubles each)
+	double *dst[10];          // the same population's ghost plane in the neighbour's lattice (peer-mapped)
+	int nmsg;
+	long long count;          // M*K
+	unsigned long long *peer_flag[2];   // the neighbours' arrival flags for data coming from this rank
+	unsigned long long value; // exchange number being published
+	unsigned int *done;       // local block counter (zero between launches)
+};
+
 struct GeomArgs
 {
 	const uint8_t *types;     // eType per cell [cells]
@@ -97,6 +109,8 @@ struct SynthArgs
 template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches);
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
+void launch_halo_push(const HaloPushArgs &a, cudaStream_t s);
+void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s);
 void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_t s);
 void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);

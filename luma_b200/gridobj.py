@@ -69,6 +69,17 @@ class GridObj:
             buf = C.create_string_buffer(unique_id, 128)
             capi.check(self._L.luma_b200_comm_init(self._h, buf), self._h)
 
+    # ---- device-initiated halo exchange (NVLink peer stores instead of NCCL send/recv) ----
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(256)
+        capi.check(self._L.luma_b200_p2p_export(self._h, buf), self._h)
+        return buf.raw
+
+    def p2p_attach(self, left_blob: bytes, right_blob: bytes):
+        capi.check(self._L.luma_b200_p2p_attach(self._h, C.create_string_buffer(left_blob, 256),
+                                                C.create_string_buffer(right_blob, 256)), self._h)
+        return self
+
     # ---- construction of the state ----
     def LBM_initGrid(self):
         """Device-side equivalent of GridObj::LBM_initGrid + body labelling for `defs`."""

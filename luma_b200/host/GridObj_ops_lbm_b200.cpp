@@ -123,6 +123,13 @@ void GridObj::LBM_multi_opt(int subcycle)
 			if (p.rank == 0) check(luma_b200_comm_unique_id(id), "comm_unique_id");
 			MPI_Bcast(id, 128, MPI_CHAR, 0, mpim->world_comm);
 			check(luma_b200_comm_init(g_dev, id), "comm_init");
+			/* device-initiated halo exchange: every rank publishes its IPC blob, takes its ring neighbours' */
+			std::vector<char> mine(LUMA_B200_P2P_BLOB_BYTES), all((size_t)LUMA_B200_P2P_BLOB_BYTES * p.nranks);
+			check(luma_b200_p2p_export(g_dev, &mine[0]), "p2p_export");
+			MPI_Allgather(&mine[0], LUMA_B200_P2P_BLOB_BYTES, MPI_CHAR, &all[0], LUMA_B200_P2P_BLOB_BYTES, MPI_CHAR, mpim->world_comm);
+			const int left = (p.rank - 1 + p.nranks) % p.nranks, right = (p.rank + 1) % p.nranks;
+			if (!getenv("LUMA_B200_HALO_NCCL"))
+				check(luma_b200_p2p_attach(g_dev, &all[(size_t)left * LUMA_B200_P2P_BLOB_BYTES], &all[(size_t)right * LUMA_B200_P2P_BLOB_BYTES]), "p2p_attach");
 		}
 #endif
 		/* wall descriptors exactly as _LBM_regularised_opt would obtain them (optimised.cpp:334) */

@@ -51,6 +51,15 @@ def broadcast_unique_id(dist, rank: int, make_id: Optional[Callable[[], bytes]] 
     return bytes(uid)
 
 
+def attach_p2p(dist, grid, rank: int, nranks: int):
+    """All-gather the ranks' IPC blobs and hand `grid` those of its ring neighbours (MPI_Allgather in a LUMA
+    MPI build): from then on its halo exchange is device-initiated (include/luma_b200.h)."""
+    blobs = [None] * nranks
+    dist.all_gather_object(blobs, grid.p2p_export())
+    grid.p2p_attach(blobs[(rank - 1) % nranks], blobs[(rank + 1) % nranks])
+    return grid
+
+
 def execute_plan_on_host(dist, plan: List[dict], lattice):
     """lattice: torch tensor [Q, P, M*K] (SoA, ghost planes 0 and P-1) on the backend's device.
     Posts every message of the plan in order as non-blocking p2p and waits (one 'group')."""

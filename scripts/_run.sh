@@ -1,12 +1,12 @@
 set -x
-# launch list of the default bench command (per-launch times are cold-cache and serialised: shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/s3_launches_c2.csv python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/s3_launches_c2.log 2>&1
-# full captures: k_bc (cavity lid), Smagorinsky k_step + k_bc of the cylinder case, time-averaging k_step
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_bc -s 5 -c 1 -o gpurun_out/s3_kbc -f python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/s3_ncu_kbc.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 5 -c 1 -o gpurun_out/s3_kstep_c4 -f python bench.py --workload c4 --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/s3_ncu_kstep_c4.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 5 -c 1 -o gpurun_out/s3_kstep_c3 -f python bench.py --workload c3 --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/s3_ncu_kstep_c3.log 2>&1
-# final bench lines
-timeout 300 python bench.py > gpurun_out/s3_bench4_n1.json 2> gpurun_out/s3_bench4_n1.err
-timeout 300 python bench.py --workload c4 --steps 300 --warmup 10 --no-cpu > gpurun_out/s3_bench4_c4_n1.json 2> gpurun_out/s3_bench4_c4_n1.err
-timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/s3_bench4_ref.json 2> gpurun_out/s3_bench4_ref.err
-ls -la gpurun_out | tail -12; cut -c1-250 gpurun_out/s3_bench4_n1.json gpurun_out/s3_bench4_c4_n1.json gpurun_out/s3_bench4_ref.json
+timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "slabs_match" 2>&1 | tail -25 > gpurun_out/s3_tests8.log
+for halo in p2p nccl; do
+for res in 256 128 64; do
+  st=300; [ $res -lt 200 ] && st=2000
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$((res/64)) bench.py --gpus 2 --steps $st --warmup 20 --halo $halo --res $res --no-e2e --no-cpu > gpurun_out/s3_halo_${halo}_${res}.json 2> gpurun_out/s3_halo_${halo}_${res}.err
+done; done
+cat gpurun_out/s3_tests8.log
+for f in gpurun_out/s3_halo_*.json; do echo $f; python -c "
+import json,sys
+d=json.load(open('$f')); print(round(d['value']), d['ms_per_step'], d['gpu_launches'])"; done
+tail -5 gpurun_out/s3_halo_p2p_256.err

@@ -24,7 +24,10 @@ def fullsize(rank, world, local, workload, steps):
     import bench
     defs = bench.workload_defs(workload, world)
     uid = ring.broadcast_unique_id(dist, rank) if world > 1 else None
-    g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid).LBM_initGrid()
+    g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
+    if world > 1:
+        ring.attach_p2p(dist, g, rank, world)
+    g.LBM_initGrid()
     g.LBM_multi_opt(steps)
     got = g.download()
     acc = []
@@ -63,12 +66,14 @@ def main():
         defs = defs_from_case(case)
         ref = port.PortGrid(case)
         Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
-        for mode in ("device_init", "upload"):
+        for mode in ("device_init", "upload", "device_init+nccl"):
             uid = ring.broadcast_unique_id(dist, rank)      # one ncclUniqueId per communicator / handle
             g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
+            if not mode.endswith("+nccl"):
+                ring.attach_p2p(dist, g, rank, world)       # device-initiated halo exchange; "+nccl" keeps send/recv
             x0, cnt = g.x_offset, g.x_count
             ref = port.PortGrid(case)
-            if mode == "device_init":
+            if mode.startswith("device_init"):
                 g.LBM_initGrid()
             else:
                 sl = slice(x0 * MK, (x0 + cnt) * MK)
@@ -101,7 +106,7 @@ def main():
             g.close(); ref.close()
         dist.barrier()
         if rank == 0:
-            print("mgpu ok: %s on %d GPUs (device_init + upload), bit-identical to the serial oracle" % (name, world), flush=True)
+            print("mgpu ok: %s on %d GPUs (device_init + upload with peer stores, device_init with NCCL), bit-identical to the serial oracle" % (name, world), flush=True)
     dist.destroy_process_group()
 
 
