@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LUMA_B200_ABI_VERSION 2
+#define LUMA_B200_ABI_VERSION 3
 
 /* ---- status codes (luma_b200_strerror gives the text; the shim maps non-zero to L_ERROR,
  *      inc/stdafx.h:135-149) ---- */
@@ -49,7 +49,7 @@ enum {
 	LUMA_B200_ECUDA         = 2,   /* CUDA runtime failure (message kept in the handle) */
 	LUMA_B200_ENCCL         = 3,   /* NCCL failure */
 	LUMA_B200_ENOMEM        = 4,   /* device or host allocation failed */
-	LUMA_B200_EUNSUPPORTED  = 5,   /* a feature outside the level-0 BGK path (KBC, BFL, IBM, refinement ...) */
+	LUMA_B200_EUNSUPPORTED  = 5,   /* a feature outside the level-0 path (BFL, IBM, refinement ...) */
 	LUMA_B200_ESTATE        = 6,   /* call order: step before upload, comm missing with nranks > 1 ... */
 	LUMA_B200_EBC_NOT_WALL  = 7,   /* a velocity/pressure site has no wall descriptor   (optimised.cpp:334-336) */
 	LUMA_B200_EBC_PRESSURE_EDGE = 8, /* pressure BC on an edge/corner                   (optimised.cpp:357-359) */
@@ -68,7 +68,7 @@ typedef struct luma_b200 luma_b200_t;
 typedef struct LumaCaseParams {
 	uint32_t struct_size;       /* sizeof(LumaCaseParams), ABI check */
 	int32_t  dims;              /* L_DIMS: 2 or 3 */
-	int32_t  num_vels;          /* L_NUM_VELS: 9 (D2Q9) or 19 (D3Q19), definitions.h:299-309 */
+	int32_t  num_vels;          /* L_NUM_VELS: 9 (D2Q9), 19 (D3Q19) or, with kbc in 3-D, 27 (D3Q27), definitions.h:299-310 */
 	int32_t  N, M, K;           /* GLOBAL level-0 size L_N, L_M, L_K (K = 1 in 2-D) */
 	int32_t  rank, nranks;      /* position in the x-ring; 0,1 for the serial build */
 	int32_t  x_offset, x_count; /* first owned global x-plane and number of owned planes
@@ -91,6 +91,9 @@ typedef struct LumaCaseParams {
 	double   re;                /* L_RE (only read with reynolds_ramp_on) */
 	int32_t  t;                 /* GridObj::t, completed iterations at upload time */
 	int32_t  time_averaged;     /* L_COMPUTE_TIME_AVERAGED_QUANTITIES (optimised.cpp:895-917) */
+	int32_t  kbc;               /* L_USE_KBC_COLLISION: _LBM_kbcCollide_opt (optimised.cpp:1122-1305) replaces _LBM_collide_opt;
+	                               KBC-D on D2Q9, KBC-N4 on D3Q27 (num_vels must be 27 in 3-D, and regularised 0 there:
+	                               src/GridObj_init_grids.cpp:266-270) */
 } LumaCaseParams;
 
 /* Wall descriptor of one velocity/pressure/slip site, exactly what GridUtils::isWithinDomainWall

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("LUMA_B200_LIB") or os.path.join(HERE, "libluma_b200.so")
 STAMP = LIB + ".srchash"
-SOURCES = ["kernels.cu", "api.cu"]
-HEADERS = ["lattice.cuh", "kernels.cuh", os.path.join("..", "..", "include", "luma_b200.h")]
+SOURCES = ["kernels_d3q19.cu", "kernels_d2q9.cu", "kernels_d3q27.cu", "kernels_common.cu", "api.cu"]
+HEADERS = ["lattice.cuh", "kernels.cuh", "kernels_impl.cuh", os.path.join("..", "..", "include", "luma_b200.h")]
 
 # -fmad=false: the reference is built without FMA contraction (makefile CFLAGS: -O3 -std=c++0x);
 # parity is bit-for-bit, so the only fused operations are the explicit fma() calls in lattice.cuh.

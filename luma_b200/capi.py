@@ -29,7 +29,7 @@ class LumaCaseParams(C.Structure):
         ("omega", C.c_double),
         ("velocity_ramp_on", C.c_int32), ("velocity_ramp", C.c_double),
         ("reynolds_ramp_on", C.c_int32), ("reynolds_ramp", C.c_double), ("re", C.c_double),
-        ("t", C.c_int32), ("time_averaged", C.c_int32),
+        ("t", C.c_int32), ("time_averaged", C.c_int32), ("kbc", C.c_int32),
     ]
 
 
@@ -128,7 +128,7 @@ def load(build_if_missing: bool = True):
     for nm in ("create", "slab", "comm_unique_id", "comm_init", "p2p_export", "p2p_attach", "upload", "init_synthetic", "step", "download",
                "download_lattyp", "download_async", "download_wait", "download_timeav", "upload_timeav", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
         getattr(L, "luma_b200_" + nm).restype = C.c_int
-    if L.luma_b200_abi_version() != 2:
+    if L.luma_b200_abi_version() != 3:
         raise ImportError("libluma_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -165,9 +165,11 @@ static void make_constants(LbmConst &C, int Q)
 	C.inv_den = 1.0 / C.den;
 	C.k1 = 1.0 - C.cs2;
 	C.k0 = 0.0 - C.cs2;
-	if (Q == 19) { C.w[0] = 1.0 / 18.0; C.w[1] = 1.0 / 36.0; C.w[2] = 1.0 / 3.0; }      // src/stdafx.cpp:140-143
+	C.w[3] = 0.0;
+	if (Q == 27) { C.w[0] = 2.0 / 27.0; C.w[1] = 1.0 / 54.0; C.w[2] = 1.0 / 216.0; C.w[3] = 8.0 / 27.0; }   // src/stdafx.cpp:130-136
+	else if (Q == 19) { C.w[0] = 1.0 / 18.0; C.w[1] = 1.0 / 36.0; C.w[2] = 1.0 / 3.0; }  // :140-143
 	else { C.w[0] = 1.0 / 9.0; C.w[1] = 1.0 / 36.0; C.w[2] = 4.0 / 9.0; }                // :147-148
-	for (int k = 0; k < 3; ++k) C.wden[k] = C.w[k] / C.den;
+	for (int k = 0; k < 4; ++k) C.wden[k] = C.w[k] / C.den;
 }
 
 static cudaEvent_t prof_event(luma_b200_t *h)
@@ -181,11 +183,15 @@ static cudaEvent_t prof_event(luma_b200_t *h)
 	return h->prof_ev[h->prof_used++];
 }
 
+// lattice dispatch: runs CALL with L bound to the lattice of a handle (L_NUM_VELS 9, 19 or 27)
+#define LAT(Q_, CALL) do { if ((Q_) == 19) { using L = D3Q19; CALL; } else if ((Q_) == 27) { using L = D3Q27; CALL; } \
+	else { using L = D2Q9; CALL; } } while (0)
+
 template <class L>
-static void main_kernel(luma_b200_t *h, const StepArgs &a, bool smag, bool force, int nplanes)
+static void main_kernel(luma_b200_t *h, const StepArgs &a, int coll, bool force, int nplanes)
 {
 	if (h->profiling && nplanes > 0) cudaEventRecord(prof_event(h), h->s_main);
-	launch_step<L>(a, smag, force, nplanes, h->s_main, &h->st.kernel_launches);
+	launch_step<L>(a, coll, force, nplanes, h->s_main, &h->st.kernel_launches);
 	if (h->profiling && nplanes > 0)
 	{
 		cudaEventRecord(prof_event(h), h->s_main);
@@ -207,7 +213,7 @@ const char *luma_b200_strerror(int code)
 	case LUMA_B200_ECUDA: return "CUDA runtime error";
 	case LUMA_B200_ENCCL: return "NCCL error";
 	case LUMA_B200_ENOMEM: return "out of memory";
-	case LUMA_B200_EUNSUPPORTED: return "feature outside the level-0 BGK/Smagorinsky path";
+	case LUMA_B200_EUNSUPPORTED: return "feature outside the level-0 BGK/Smagorinsky/KBC path";
 	case LUMA_B200_ESTATE: return "call out of order";
 	case LUMA_B200_EBC_NOT_WALL: return "Trying to apply a regularised BC on a site not within a wall.";
 	case LUMA_B200_EBC_PRESSURE_EDGE: return "Pressure BC cannot be applied to a corner or an edge.";
@@ -279,8 +285,10 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	if (!out || !p) return LUMA_B200_EINVAL;
 	*out = nullptr;
 	if (p->struct_size != sizeof(LumaCaseParams)) return LUMA_B200_EINVAL;
-	if (!((p->dims == 3 && p->num_vels == 19) || (p->dims == 2 && p->num_vels == 9)))
-		return (p->num_vels == 27) ? LUMA_B200_EUNSUPPORTED : LUMA_B200_EINVAL;
+	// L_NUM_VELS follows from L_DIMS and L_USE_KBC_COLLISION (inc/definitions.h:299-310)
+	if (!((p->dims == 3 && p->num_vels == (p->kbc ? 27 : 19)) || (p->dims == 2 && p->num_vels == 9))) return LUMA_B200_EINVAL;
+	// "Cannot use regularised boundaries with D3Q27 because of the corner treatment" (src/GridObj_init_grids.cpp:266-270)
+	if (p->num_vels == 27 && p->regularised) return LUMA_B200_EINVAL;
 	if (p->N < 1 || p->M < 2 || p->K < 1 || (p->dims == 2 && p->K != 1)) return LUMA_B200_EINVAL;
 	if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return LUMA_B200_EINVAL;
 	if (p->x_count < 1 || p->x_offset < 0 || p->x_offset + p->x_count > p->N) return LUMA_B200_EINVAL;
@@ -458,12 +466,13 @@ static int ensure_staging(luma_b200_t *h, size_t bytes)
 }
 
 // populations with c_x = +1 travel to the +x neighbour, c_x = -1 to the -x neighbour
-static int edge_pops(int Q, int sign, int out[8])
+static int edge_pops(int Q, int sign, int out[9])
 {
 	int n = 0;
 	for (int v = 0; v < Q; ++v)
 	{
-		const int cx = (Q == 19) ? D3Q19::c(v, 0) : D2Q9::c(v, 0);
+		int cx = 0;
+		LAT(Q, cx = L::c(v, 0));
 		if (cx == sign) out[n++] = v;
 	}
 	return n;
@@ -476,7 +485,7 @@ static int build_halo_plan(const LumaCaseParams &p, std::vector<LumaHaloMsg> &pl
 	plan.clear();
 	if (p.nranks < 2) return 0;
 	const int n = p.nranks, right = (p.rank + 1) % n, left = (p.rank - 1 + n) % n;
-	int plus[8], minus[8];
+	int plus[9], minus[9];
 	const int np = edge_pops(p.num_vels, +1, plus), nm = edge_pops(p.num_vels, -1, minus);
 	const int P = p.x_count + 2;
 	for (int a = 0; a < np; ++a) plan.push_back({ 1, right, plus[a], P - 2 });
@@ -499,7 +508,9 @@ static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s)
 		if (!m.is_send) continue;
 		// c_x = +1 populations go to the right neighbour's low ghost plane (0), c_x = -1 populations to the left
 		// neighbour's high ghost plane (P_left - 1); with two ranks both neighbours are the same GPU
-		const bool to_right = ((h->Q == 19) ? D3Q19::c(m.pop, 0) : D2Q9::c(m.pop, 0)) > 0;
+		int cx = 0;
+		LAT(h->Q, cx = L::c(m.pop, 0));
+		const bool to_right = cx > 0;
 		const PeerMap &pm = h->peer[to_right ? 1 : 0];
 		const int dst_plane = to_right ? 0 : pm.P - 1;
 		a.src[a.nmsg] = h->f[li] + (long long)m.pop * h->stride + (long long)m.plane * h->MK;
@@ -563,7 +574,7 @@ static int exchange_ghost_planes(luma_b200_t *h, cudaStream_t s)
 	return LUMA_B200_OK;
 }
 
-static inline int lat_c(int Q, int v, int d) { return (Q == 19) ? D3Q19::c(v, d) : D2Q9::c(v, d); }
+static inline int lat_c(int Q, int v, int d) { int c = 0; LAT(Q, c = L::c(v, d)); return c; }
 
 // after h->types (owned planes) and h->bcdesc exist on the device: ghost planes, validation of the
 // boundary sites the way the reference would L_ERROR on them, the list of sites k_bc handles, cell words.
@@ -739,9 +750,15 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 	g.P = h->P; g.M = p.M; g.K = p.K; g.wrap_x = h->ghost ? 0 : 1;
 	g.p_begin = pb; g.p_end = pe;
 	g.regularised = reg ? 1 : 0;
-	if (h->Q == 19) launch_cell_words<D3Q19>(g, h->s_main); else launch_cell_words<D2Q9>(g, h->s_main);
+	LAT(h->Q, launch_cell_words<L>(g, h->s_main));
 	h->st.kernel_launches++;
-	if (!forced.empty()) { launch_force_general(h->cw, forced_dev, (int)forced.size(), h->s_main); h->st.kernel_launches++; }
+	if (!forced.empty())
+	{
+		int class_shift = 0;
+		LAT(h->Q, class_shift = CW<L>::CLASS_SHIFT);
+		launch_force_general(h->cw, forced_dev, (int)forced.size(), class_shift, h->s_main);
+		h->st.kernel_launches++;
+	}
 	const cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(h->s_main);
 	cudaFree(forced_dev);
 	CK(e1); CK(e2);
@@ -772,8 +789,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	{
 		const long long n = std::min(chunk, owned - c0);
 		CK(cudaMemcpyAsync(h->staging, f_aos + (host_off + c0) * h->Q, (size_t)n * h->Q * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
-		if (h->Q == 19) launch_aos_to_soa<D3Q19>((const double *)h->staging, h->f[0], h->stride, dev_off + c0, n, h->s_main);
-		else launch_aos_to_soa<D2Q9>((const double *)h->staging, h->f[0], h->stride, dev_off + c0, n, h->s_main);
+		LAT(h->Q, launch_aos_to_soa<L>((const double *)h->staging, h->f[0], h->stride, dev_off + c0, n, h->s_main));
 		h->st.kernel_launches++;
 	}
 	for (long long c0 = 0; c0 < owned; c0 += chunk)
@@ -890,7 +906,7 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	a.rhoin = p.rhoin;
 	a.no_flow = c->no_flow; a.has_box = c->has_box;
 	a.C = h->C;
-	if (h->Q == 19) launch_synthetic<D3Q19>(a, h->s_main); else launch_synthetic<D2Q9>(a, h->s_main);
+	LAT(h->Q, launch_synthetic<L>(a, h->s_main));
 	h->st.kernel_launches++;
 	CK(cudaGetLastError());
 	h->cur = 0;
@@ -934,7 +950,8 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	if (nsteps == 0) return LUMA_B200_OK;
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
-	const bool smag = p.bgksmag != 0, force = p.gravity_on != 0;
+	const bool force = p.gravity_on != 0;
+	const int coll = p.kbc ? 2 : (p.bgksmag ? 1 : 0);      // optimised.cpp:147-151: the KBC operator replaces _LBM_collide_opt
 
 	StepArgs a;
 	memset(&a, 0, sizeof(a));
@@ -944,14 +961,12 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	a.C = h->C;
 	for (int v = 0; v < h->Q; ++v)
 	{
-		const int cx = (h->Q == 19) ? D3Q19::c(v, 0) : D2Q9::c(v, 0);
-		const int cy = (h->Q == 19) ? D3Q19::c(v, 1) : D2Q9::c(v, 1);
-		const int cz = (h->Q == 19) ? D3Q19::c(v, 2) : D2Q9::c(v, 2);
+		const int cx = lat_c(h->Q, v, 0), cy = lat_c(h->Q, v, 1), cz = lat_c(h->Q, v, 2);
 		a.off_pull[v] = 8LL * ((long long)v * h->stride - ((long long)cx * h->MK + (long long)cy * p.K + cz));
 	}
 	a.bc_list = h->bc_list; a.bc_extra = h->bc_extra; a.n_bc = h->n_bc; a.uin = h->uin;
 	a.rho_out = p.rho_out;
-	a.types = h->types; a.general = h->general ? 1 : 0; a.regularised = p.regularised ? 1 : 0;
+	a.types = h->types; a.bcdesc = h->bcdesc; a.general = h->general ? 1 : 0; a.regularised = p.regularised ? 1 : 0;
 	a.velramp_on = p.velocity_ramp_on ? 1 : 0;
 	a.tav = h->tav;
 	// force_xyz = rho_init * gravity * refinement_ratio along L_GRAVITY_DIRECTION (init_grids.cpp:296-297)
@@ -975,7 +990,9 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		}
 		x.omega = h->omega;
 		x.tau = 1.0 / h->omega;
-		for (int k = 0; k < 3; ++k) x.lam[k] = (1 - 0.5 * h->omega) * (h->C.w[k] / h->C.cs2);
+		for (int k = 0; k < 4; ++k) x.lam[k] = (1 - 0.5 * h->omega) * (h->C.w[k] / h->C.cs2);
+		x.kbc_beta_m1 = 2.0 / h->omega;
+		x.kbc_inv_beta = 1.0 / x.kbc_beta_m1;
 		x.ramp = velocity_ramp_coef(p, (t_now + 1) * p.dt);
 		x.ramp_t = velocity_ramp_coef(p, t_now * p.dt);
 		x.t_now = (double)t_now; x.t_next = (double)(t_now + 1);
@@ -994,19 +1011,16 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		x.p0 = 0; x.pstep = 1;
 		if (!side)
 		{
-			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_main, &h->st.kernel_launches);
-			else launch_bc<D2Q9>(x, smag, force, h->s_main, &h->st.kernel_launches);
+			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_main, &h->st.kernel_launches));
 		}
 		if (side)
 		{
 			CK(cudaEventRecord(h->ev_fork, h->s_main));
 			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
-			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_comm, &h->st.kernel_launches);
-			else launch_bc<D2Q9>(x, smag, force, h->s_comm, &h->st.kernel_launches);
+			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
 			CK(cudaEventRecord(h->ev_comm, h->s_comm));
 		}
-		if (h->Q == 19) main_kernel<D3Q19>(h, x, smag, force, h->P);
-		else main_kernel<D2Q9>(h, x, smag, force, h->P);
+		LAT(h->Q, main_kernel<L>(h, x, coll, force, h->P));
 		if (side) CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
 	}
 	else
@@ -1021,25 +1035,21 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		in.p0 = 2; in.pstep = 1;
 		if (!side)
 		{
-			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_main, &h->st.kernel_launches);
-			else launch_bc<D2Q9>(x, smag, force, h->s_main, &h->st.kernel_launches);
+			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_main, &h->st.kernel_launches));
 		}
 		if (side)
 		{
 			CK(cudaEventRecord(h->ev_fork, h->s_main));
 			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
-			if (h->Q == 19) launch_bc<D3Q19>(x, smag, force, h->s_comm, &h->st.kernel_launches);
-			else launch_bc<D2Q9>(x, smag, force, h->s_comm, &h->st.kernel_launches);
+			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
 		}
-		if (h->Q == 19) launch_step<D3Q19>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches);
-		else launch_step<D2Q9>(e, smag, force, nedge, h->s_main, &h->st.kernel_launches);
+		LAT(h->Q, launch_step<L>(e, coll, force, nedge, h->s_main, &h->st.kernel_launches));
 		CK(cudaEventRecord(h->ev_edge, h->s_main));
 		CK(cudaStreamWaitEvent(h->s_comm, h->ev_edge, 0));
 		int rc = exchange_populations(h, h->f[h->cur ^ 1], h->s_comm);
 		if (rc) return rc;
 		CK(cudaEventRecord(h->ev_comm, h->s_comm));
-		if (h->Q == 19) main_kernel<D3Q19>(h, in, smag, force, owned - 2);
-		else main_kernel<D2Q9>(h, in, smag, force, owned - 2);
+		LAT(h->Q, main_kernel<L>(h, in, coll, force, owned - 2));
 	}
 		return LUMA_B200_OK;
 	};
@@ -1112,8 +1122,7 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 			vs.list = h->vel_list; vs.n = h->n_vel; vs.types = h->types; vs.bcdesc = h->bcdesc; vs.u = h->u; vs.stride = h->stride;
 			vs.uin = h->uin; vs.ramp_t = a.ramp_t;
 			vs.P = h->P; vs.M = p.M; vs.K = p.K; vs.N = p.N; vs.wrap_x = a.wrap_x; vs.x_first = p.x_offset - h->ghost;
-			if (h->Q == 19) launch_velsrc<D3Q19>(vs, h->s_main, &h->st.kernel_launches);
-			else launch_velsrc<D2Q9>(vs, h->s_main, &h->st.kernel_launches);
+			LAT(h->Q, launch_velsrc<L>(vs, h->s_main, &h->st.kernel_launches));
 		}
 		h->cur ^= 1;
 		++h->t;
@@ -1142,7 +1151,7 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	h->st.ms_last_call = ms;
 	h->st.ms_per_step = ms / nsteps;
 	h->st.mlups_last_call = (double)h->st.cells * nsteps / ((double)ms * 1e3);
-	int plus[8];
+	int plus[9];
 	h->st.halo_bytes_per_step = h->ghost ? 2LL * edge_pops(h->Q, +1, plus) * h->MK * (long long)sizeof(double) : 0;
 	return LUMA_B200_OK;
 }
@@ -1165,8 +1174,7 @@ int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_ao
 		for (long long c0 = 0; c0 < owned; c0 += chunk)
 		{
 			const long long n = std::min(chunk, owned - c0);
-			if (h->Q == 19) launch_soa_to_aos<D3Q19>(h->f[h->cur], (double *)h->staging, h->stride, dev_off + c0, n, h->s_main);
-			else launch_soa_to_aos<D2Q9>(h->f[h->cur], (double *)h->staging, h->stride, dev_off + c0, n, h->s_main);
+			LAT(h->Q, launch_soa_to_aos<L>(h->f[h->cur], (double *)h->staging, h->stride, dev_off + c0, n, h->s_main));
 			h->st.kernel_launches++;
 			CK(cudaMemcpyAsync(f_aos + (host_off + c0) * h->Q, h->staging, (size_t)n * h->Q * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
 		}
@@ -1222,8 +1230,7 @@ int luma_b200_download_async(luma_b200_t *h, int32_t halo, unsigned what, double
 	}
 	if (what & LUMA_B200_F)
 	{
-		if (h->Q == 19) launch_soa_to_aos<D3Q19>(h->f[h->cur], s_f, h->stride, dev_off, owned, h->s_main);
-		else launch_soa_to_aos<D2Q9>(h->f[h->cur], s_f, h->stride, dev_off, owned, h->s_main);
+		LAT(h->Q, launch_soa_to_aos<L>(h->f[h->cur], s_f, h->stride, dev_off, owned, h->s_main));
 		h->st.kernel_launches++;
 	}
 	CK(cudaGetLastError());
@@ -1337,8 +1344,7 @@ int luma_b200_forces(luma_b200_t *h, double F[3])
 	CK(cudaSetDevice(p.device));
 	const double *prev = h->f[h->cur ^ 1];
 	int nb;
-	if (h->Q == 19) nb = launch_momex<D3Q19>(prev, h->types, h->stride, h->P, p.M, p.K, h->ghost, h->P - h->ghost, p.x_offset - h->ghost, p.N, h->momex_dev, 4096, h->s_main);
-	else nb = launch_momex<D2Q9>(prev, h->types, h->stride, h->P, p.M, p.K, h->ghost, h->P - h->ghost, p.x_offset - h->ghost, p.N, h->momex_dev, 4096, h->s_main);
+	LAT(h->Q, nb = launch_momex<L>(prev, h->types, h->stride, h->P, p.M, p.K, h->ghost, h->P - h->ghost, p.x_offset - h->ghost, p.N, h->momex_dev, 4096, h->s_main));
 	h->st.kernel_launches++;
 	std::vector<double> part((size_t)3 * nb);
 	CK(cudaMemcpyAsync(part.data(), h->momex_dev, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
@@ -1359,7 +1365,7 @@ int luma_b200_stats(luma_b200_t *h, LumaStats *s)
 int luma_b200_halo_plan(const LumaCaseParams *p, LumaHaloMsg *msgs, int32_t capacity, int32_t *count)
 {
 	if (!p || !count || p->struct_size != sizeof(LumaCaseParams)) return LUMA_B200_EINVAL;
-	if (!((p->dims == 3 && p->num_vels == 19) || (p->dims == 2 && p->num_vels == 9))) return LUMA_B200_EINVAL;
+	if (!((p->dims == 3 && (p->num_vels == 19 || p->num_vels == 27)) || (p->dims == 2 && p->num_vels == 9))) return LUMA_B200_EINVAL;
 	if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks || p->x_count < 1) return LUMA_B200_EINVAL;
 	std::vector<LumaHaloMsg> plan;
 	const int n = build_halo_plan(*p, plan);

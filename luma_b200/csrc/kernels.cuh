@@ -14,7 +14,7 @@ struct StepArgs
 	double *rho;              // [cells]
 	double *u;                // SoA [D][stride]
 	long long stride;         // elements between populations (>= cells, multiple of 16)
-	long long off_pull[19];   // BYTE offset 8*(v*stride - (cx*M*K + cy*K + cz)): where population v is pulled from (no wrap, no bounce-back)
+	long long off_pull[27];   // BYTE offset 8*(v*stride - (cx*M*K + cy*K + cz)): where population v is pulled from (no wrap, no bounce-back)
 	int P, M, K;              // local planes (incl. ghost planes when !wrap_x), rows, columns
 	unsigned MK;              // M*K
 	int wrap_x;               // 1: periodic wrap inside the array (single rank); 0: ghost planes 0 and P-1
@@ -23,7 +23,9 @@ struct StepArgs
 	double omega;
 	double tau;               // 1.0 / omega
 	double smag_coef;         // 2.0*L_SQRT2*SQ(L_CSMAG)*L_RHOIN*SQ(cs)*SQ(cs)          optimised.cpp:752
-	double lam[3];            // (1 - 0.5*omega) * (w/(cs*cs)) per weight class            optimised.cpp:962
+	double lam[4];            // (1 - 0.5*omega) * (w/(cs*cs)) per weight class            optimised.cpp:962
+	double kbc_beta_m1;       // 2.0 / omega                                               optimised.cpp:1279
+	double kbc_inv_beta;      // 1.0 / kbc_beta_m1                                         optimised.cpp:1293
 	double F[3];              // force_xyz (uniform: rho_init * gravity along one axis)    init_grids.cpp:296
 	double hF[3];             // 0.5 * F
 	LbmConst C;
@@ -37,6 +39,7 @@ struct StepArgs
 	double rho_out;
 	// per-link handling of class-4 sites (and of regularised sites when `general` is set)
 	const uint8_t *types;     // eType per cell
+	const uint32_t *bcdesc;   // wall descriptors per cell (read by lattices whose cell word has no room for them)
 	int general;              // the grid has eSlip / eExtrapolateRight / forced-equilibrium sources
 	int regularised;          // L_REGULARISED_BOUNDARIES
 	int velramp_on;           // L_VELOCITY_RAMP defined: forced-equilibrium sources take u = u_in[j]*ramp_t
@@ -64,8 +67,8 @@ struct VelSrcArgs
 // ---- device-initiated halo exchange over NVLink peer memory (kernels.cu k_halo_push / k_halo_wait) ----
 struct HaloPushArgs
 {
-	const double *src[10];    // local: one population plane of the lattice just written (M*K doubles each)
-	double *dst[10];          // the same population's ghost plane in the neighbour's lattice (peer-mapped)
+	const double *src[18];    // local: one population plane of the lattice just written (M*K doubles each)
+	double *dst[18];          // the same population's ghost plane in the neighbour's lattice (peer-mapped)
 	int nmsg;
 	long long count;          // M*K
 	unsigned long long *peer_flag[2];   // the neighbours' arrival flags for data coming from this rank
@@ -106,12 +109,13 @@ struct SynthArgs
 	LbmConst C;
 };
 
-template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches);
-template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches);
+// coll: 0 BGK, 1 BGK + Smagorinsky, 2 KBC (D2Q9 and D3Q27 only; D3Q27 always)
+template <class L> void launch_step(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches);
+template <class L> void launch_bc(const StepArgs &a, int coll, bool force, cudaStream_t s, int64_t *launches);
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
 void launch_halo_push(const HaloPushArgs &a, cudaStream_t s);
 void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s);
-void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_t s);
+void launch_force_general(uint32_t *cw, const long long *ids, int n, int class_shift, cudaStream_t s);
 void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);

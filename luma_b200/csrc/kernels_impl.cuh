@@ -1,4 +1,6 @@
-// kernels.cu -- sm_100a device code of the level-0 LBM time step (compiled with -fmad=false).
+// kernels_impl.cuh -- sm_100a device code of the level-0 LBM time step, templated on the lattice (compiled
+// with -fmad=false).  Included by one translation unit per lattice (kernels_d2q9.cu, kernels_d3q19.cu,
+// kernels_d3q27.cu: they build in parallel) and by kernels_common.cu for the layout-conversion templates.
 //
 // One step = k_step over all planes (fluid sites) + k_bc over the list of velocity/pressure sites.
 // Both read lattice `fin` and write lattice `fout` (two-lattice pull scheme, SoA populations), so
@@ -8,6 +10,7 @@
 //
 // Reference for every function: /root/reference/LUMA/src/GridObj_ops_lbm_optimised.cpp (cited as
 // optimised.cpp below).
+#pragma once
 #include "kernels.cuh"
 
 namespace luma {
@@ -22,6 +25,9 @@ namespace luma {
 #ifndef LUMA_MIN_BLOCKS_SMAG
 #define LUMA_MIN_BLOCKS_SMAG 5  /* measured on B200: 5 x 128 threads (<= 102 registers, no spills) beats 4 and 3; 6 spills */
 #endif
+#ifndef LUMA_MIN_BLOCKS_KBC
+#define LUMA_MIN_BLOCKS_KBC 3   /* KBC keeps the own-site populations, ds and dh alive beside feq */
+#endif
 #ifndef LUMA_LOAD_MODE
 #define LUMA_LOAD_MODE 0      /* 0 ld.global.nc (__ldg), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate, 3 plain */
 #endif
@@ -29,6 +35,12 @@ namespace luma {
 #define LUMA_STORE_MODE 0     /* 0 plain, 1 st.global.cs, 2 st.global.L1::no_allocate */
 #endif
 constexpr int STEP_THREADS = LUMA_STEP_THREADS;
+// collision operator of a kernel instantiation: L_USE_BGKSMAG / L_USE_KBC_COLLISION (optimised.cpp:147-151, :769-773)
+enum : int { COLL_BGK = 0, COLL_SMAG = 1, COLL_KBC = 2 };
+template <class L, int COLL> constexpr int step_min_blocks()
+{
+	return COLL == COLL_SMAG ? LUMA_MIN_BLOCKS_SMAG : (COLL == COLL_KBC ? (L::Q == 27 ? 2 : LUMA_MIN_BLOCKS_KBC) : LUMA_MIN_BLOCKS);
+}
 
 __device__ __forceinline__ double load_pop(const double *p)
 {
@@ -66,7 +78,7 @@ __device__ __forceinline__ void pull_populations(const StepArgs &a, const int p,
 {
 	const double *base = a.fin + id;
 	const bool x_wraps = a.wrap_x && (p == 0 || p == a.P - 1);
-	if ((w & (CW_LINKS | CW_EDGE)) == 0 && !x_wraps)
+	if ((w & (CW<L>::LINKS | CW<L>::EDGE)) == 0 && !x_wraps)
 	{
 		// interior site with fluid neighbours only (the overwhelmingly common case): kernel-uniform offsets
 		const char *pb = reinterpret_cast<const char *>(base);
@@ -81,7 +93,7 @@ __device__ __forceinline__ void pull_populations(const StepArgs &a, const int p,
 		if (p == a.P - 1) xp = -(long long)(a.P - 1) * a.MK;
 	}
 	long long ym = -(long long)a.K, yp = (long long)a.K, zm = -1, zp = 1;
-	if (w & CW_EDGE)
+	if (w & CW<L>::EDGE)
 	{
 		const unsigned j = r / (unsigned)a.K, k = r - j * (unsigned)a.K;
 		if (j == 0) ym = (long long)(a.M - 1) * a.K;
@@ -109,12 +121,30 @@ __device__ __forceinline__ void pull_populations(const StepArgs &a, const int p,
 	}
 }
 
-// BGK(/Smagorinsky) collision with optional Guo forcing, GridObj::_LBM_collide_opt (optimised.cpp:765-790)
-template <class L, bool SMAG, bool FORCE>
-__device__ __forceinline__ void collide(const StepArgs &a, const double (&u)[3], const double (&feq)[L::Q], double (&f)[L::Q])
+// the populations of the previous time level at the site itself (what the reference's KBC operator collides)
+template <class L>
+__device__ __forceinline__ void load_own(const StepArgs &a, const long long id, double (&fo)[L::Q])
 {
+	const char *pb = reinterpret_cast<const char *>(a.fin + id);
+	const long long sb = a.stride * (long long)sizeof(double);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v) fo[v] = load_pop(reinterpret_cast<const double *>(pb + (long long)v * sb));
+}
+
+// BGK(/Smagorinsky) collision with optional Guo forcing, GridObj::_LBM_collide_opt (optimised.cpp:765-790),
+// or the KBC operator _LBM_kbcCollide_opt (:1122-1305), which replaces f by the collided own-site populations
+template <class L, int COLL, bool FORCE>
+__device__ __forceinline__ void collide(const StepArgs &a, const long long id, const double (&u)[3], const double (&feq)[L::Q], double (&f)[L::Q])
+{
+	if constexpr (COLL == COLL_KBC)
+	{
+		double fo[L::Q];
+		load_own<L>(a, id, fo);
+		kbc_collide<L, FORCE>(u, feq, fo, a.kbc_beta_m1, a.kbc_inv_beta, a.F, a.C, a.lam, f);
+		return;
+	}
 	double omega_s = a.omega;
-	if (SMAG) omega_s = smagorinsky_omega<L>(f, feq, a.tau, a.smag_coef);
+	if (COLL == COLL_SMAG) omega_s = smagorinsky_omega<L>(f, feq, a.tau, a.smag_coef);
 #pragma unroll
 	for (int v = 0; v < L::Q; ++v)
 	{
@@ -144,11 +174,11 @@ __device__ __forceinline__ void store_populations(const StepArgs &a, const long 
 // ------------------------------------------------------------------------------------------------
 template <class L>
 __device__ __noinline__ void pull_general(const StepArgs &a, const int p, const int j, const int k, const long long id,
-	const uint32_t w, const uint8_t type, double (&f)[L::Q])
+	const uint32_t desc, const uint8_t type, double (&f)[L::Q])
 {
 	int n[3];
 #pragma unroll
-	for (int d = 0; d < 3; ++d) n[d] = (int)((w >> (CW_N_SHIFT + 2 * d)) & 3u) - 1;
+	for (int d = 0; d < 3; ++d) n[d] = (int)((desc >> (CW_N_SHIFT + 2 * d)) & 3u) - 1;
 	const double *fin = a.fin;
 #pragma unroll
 	for (int v = 0; v < L::Q; ++v)
@@ -185,12 +215,21 @@ __device__ __noinline__ void pull_general(const StepArgs &a, const int p, const 
 	}
 }
 
+// wall descriptor of a site (normalDirection, normal vector, edgeCount at bits 22..31): part of the cell word
+// where it fits, else the per-site descriptor array
+template <class L>
+__device__ __forceinline__ uint32_t site_desc(const StepArgs &a, const long long id, const uint32_t w)
+{
+	if constexpr (L::DESC_IN_WORD) return w;
+	else return a.bcdesc[id];
+}
+
 // stream of a site handled by k_bc: the fast path unless the grid holds special types
 template <class L>
 __device__ __forceinline__ void pull_any(const StepArgs &a, const int p, const unsigned r, const int j, const int k,
 	const long long id, const uint32_t w, double (&f)[L::Q])
 {
-	if (a.general && cw_class(w) != CLS_FLUID) pull_general<L>(a, p, j, k, id, w, a.types[id], f);
+	if (a.general && cw_class<L>(w) != CLS_FLUID) pull_general<L>(a, p, j, k, id, site_desc<L>(a, id, w), a.types[id], f);
 	else pull_populations<L>(a, p, r, id, w, f);
 }
 
@@ -236,22 +275,22 @@ __device__ __forceinline__ void tavg_update(const StepArgs &a, const long long i
 // ------------------------------------------------------------------------------------------------
 // the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
 // ------------------------------------------------------------------------------------------------
-template <class L, bool SMAG, bool FORCE, bool TAVG>
-__global__ void __launch_bounds__(STEP_THREADS, SMAG ? LUMA_MIN_BLOCKS_SMAG : LUMA_MIN_BLOCKS) k_step(const StepArgs a)
+template <class L, int COLL, bool FORCE, bool TAVG>
+__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_step(const StepArgs a)
 {
 	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
 	if (r >= a.MK) return;
 	const int p = a.p0 + (int)blockIdx.y * a.pstep;
 	const long long id = (long long)p * a.MK + r;
 	const uint32_t w = __ldg(a.cw + id);
-	if (cw_class(w) != CLS_FLUID) return;
+	if (cw_class<L>(w) != CLS_FLUID) return;
 
 	double f[L::Q], feq[L::Q], u[3], rho;
 	pull_populations<L>(a, p, r, id, w, f);
 	macroscopic<L, FORCE>(f, a.hF, rho, u);
 	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
 	equilibrium_all<L>(rho, u, a.C, feq);
-	collide<L, SMAG, FORCE>(a, u, feq, f);
+	collide<L, COLL, FORCE>(a, id, u, feq, f);
 	store_populations<L>(a, id, f);
 	if (a.write_macro)
 	{
@@ -270,7 +309,7 @@ __device__ __noinline__ void neighbour_macro(const StepArgs &a, const int p, con
 	const unsigned r = (unsigned)j * (unsigned)a.K + (unsigned)k;
 	const long long id = (long long)p * a.MK + r;
 	const uint32_t w = a.cw[id];
-	const uint32_t cls = cw_class(w);
+	const uint32_t cls = cw_class<L>(w);
 	if (cls == CLS_FLUID || cls == CLS_GENERAL)      // upload guarantees the neighbour is eFluid or eSolid
 	{
 		double f[L::Q];
@@ -291,16 +330,17 @@ __device__ __noinline__ void neighbour_macro(const StepArgs &a, const int p, con
 // pull and the store of one site; (r1,u1), (r2,u2) are the new-time moments of the two inward
 // neighbours (only read for pressure faces and velocity edges/corners).
 // ------------------------------------------------------------------------------------------------
+template <class L>
 __device__ __forceinline__ bool bc_needs_neighbours(const uint32_t w)
 {
-	return (w >> CW_EC_SHIFT) > 1u || cw_class(w) == CLS_PRESSURE;
+	return (w >> CW_EC_SHIFT) > 1u || cw_class<L>(w) == CLS_PRESSURE;
 }
 
-template <class L, bool SMAG, bool FORCE>
-__device__ __forceinline__ void bc_regularise(const StepArgs &a, const uint32_t w, const int j, double (&f)[L::Q],
+template <class L, int COLL, bool FORCE>
+__device__ __forceinline__ void bc_regularise(const StepArgs &a, const long long id, const uint32_t w, const int j, double (&f)[L::Q],
 	const double r1, const double (&u1)[3], const double r2, const double (&u2)[3], double &dens, double (&uw)[3])
 {
-	const bool pressure = cw_class(w) == CLS_PRESSURE;
+	const bool pressure = cw_class<L>(w) == CLS_PRESSURE;
 	const int ec = (int)(w >> CW_EC_SHIFT);
 	const int nd = (int)((w >> CW_ND_SHIFT) & 3u);
 	int n[3];
@@ -395,18 +435,18 @@ __device__ __forceinline__ void bc_regularise(const StepArgs &a, const uint32_t 
 			);
 	}
 	// macro is skipped for these types (:803-806); force and collide are applied (:138-150)
-	collide<L, SMAG, FORCE>(a, uw, feq, f);
+	collide<L, COLL, FORCE>(a, id, uw, feq, f);
 }
 
 // class-4 sites: stream per link, macro only for eFluid/eSlip (optimised.cpp:803-806; every other type
 // keeps its stored rho,u), force, collide
-template <class L, bool SMAG, bool FORCE, bool TAVG>
+template <class L, int COLL, bool FORCE, bool TAVG>
 __device__ __noinline__ void general_site(const StepArgs &a, const int p, const int j, const int k, const long long id,
 	const uint32_t w, const int reps)
 {
 	const uint8_t type = a.types[id];
 	double f[L::Q], feq[L::Q], u[3], rho;
-	pull_general<L>(a, p, j, k, id, w, type, f);
+	pull_general<L>(a, p, j, k, id, site_desc<L>(a, id, w), type, f);
 	if (type == T_FLUID || type == T_SLIP) macroscopic<L, FORCE>(f, a.hF, rho, u);
 	else
 	{
@@ -416,14 +456,14 @@ __device__ __noinline__ void general_site(const StepArgs &a, const int p, const 
 	}
 	if (TAVG) tavg_update<L>(a, id, rho, u, reps);
 	equilibrium_all<L>(rho, u, a.C, feq);
-	collide<L, SMAG, FORCE>(a, u, feq, f);
+	collide<L, COLL, FORCE>(a, id, u, feq, f);
 	store_populations<L>(a, id, f);
 	a.rho[id] = rho;
 #pragma unroll
 	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
 }
 
-template <class L, bool SMAG, bool FORCE, bool TAVG>
+template <class L, int COLL, bool FORCE, bool TAVG>
 __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -434,17 +474,18 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 	const int j = (int)(r / (unsigned)a.K), k = (int)(r - (unsigned)j * (unsigned)a.K);
 	const uint32_t w = a.cw[id];
 	const int reps = 1 + ((TAVG && a.bc_extra) ? a.bc_extra[t] : 0);
-	if (cw_class(w) == CLS_GENERAL)
+	if (!L::REGULARISABLE || cw_class<L>(w) == CLS_GENERAL)
 	{
-		general_site<L, SMAG, FORCE, TAVG>(a, p, j, k, id, w, reps);
+		general_site<L, COLL, FORCE, TAVG>(a, p, j, k, id, w, reps);
 		return;
 	}
-
+	if constexpr (L::REGULARISABLE)
+	{
 	double f[L::Q];
 	pull_any<L>(a, p, r, j, k, id, w, f);
 
 	double r1 = 0.0, r2 = 0.0, u1[3] = { 0.0, 0.0, 0.0 }, u2[3] = { 0.0, 0.0, 0.0 };
-	if (bc_needs_neighbours(w))
+	if (bc_needs_neighbours<L>(w))
 	{
 		int n[3];
 #pragma unroll
@@ -453,13 +494,14 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 		neighbour_macro<L, FORCE>(a, p + 2 * n[0], j + 2 * n[1], k + 2 * n[2], r2, u2);
 	}
 	double dens, uw[3];
-	bc_regularise<L, SMAG, FORCE>(a, w, j, f, r1, u1, r2, u2, dens, uw);
+	bc_regularise<L, COLL, FORCE>(a, id, w, j, f, r1, u1, r2, u2, dens, uw);
 	if (TAVG) tavg_update<L>(a, id, dens, uw, reps);      // _LBM_macro_opt still runs its averaging tail for these types
 
 	a.rho[id] = dens;
 #pragma unroll
 	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = uw[d];
 	store_populations<L>(a, id, f);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -519,46 +561,27 @@ template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64
 	if (launches) ++*launches;
 }
 
-// sites the host wants handled per link (class 4) although they are eFluid
-__global__ void k_force_general(uint32_t *cw, const long long *ids, int n)
-{
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
-	const uint32_t w = cw[ids[t]];
-	if (cw_class(w) == CLS_FLUID) cw[ids[t]] = (w & ~(CW_CLASS_MASK << CW_CLASS_SHIFT)) | (CLS_GENERAL << CW_CLASS_SHIFT);
-}
-void launch_force_general(uint32_t *cw, const long long *ids, int n, cudaStream_t s)
-{
-	if (n > 0) k_force_general<<<(n + 127) / 128, 128, 0, s>>>(cw, ids, n);
-}
-
-__global__ void k_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n)
-{
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < n) out[ids[t]] = vals[t];
-}
-void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s)
-{
-	if (n > 0) k_scatter_u32<<<(n + 127) / 128, 128, 0, s>>>(out, ids, vals, n);
-}
-
-#define LUMA_DISPATCH(KERNEL, GRID, THREADS) \
+// kernel variant = collision operator x Guo forcing x time averages; the reference ties KBC to D2Q9 / D3Q27 and
+// D3Q27 to KBC (inc/definitions.h:299-310), so only those combinations are instantiated
+#define LUMA_DISPATCH_FT(KERNEL, COLL, GRID, THREADS) \
 	do { \
-		const int key = (smag ? 4 : 0) | (force ? 2 : 0) | (a.tav ? 1 : 0); \
-		switch (key) \
+		switch ((force ? 2 : 0) | (a.tav ? 1 : 0)) \
 		{ \
-		case 0: KERNEL<L, false, false, false><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 1: KERNEL<L, false, false, true><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 2: KERNEL<L, false, true, false><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 3: KERNEL<L, false, true, true><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 4: KERNEL<L, true, false, false><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 5: KERNEL<L, true, false, true><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 6: KERNEL<L, true, true, false><<<GRID, THREADS, 0, s>>>(a); break; \
-		default: KERNEL<L, true, true, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 0: KERNEL<L, COLL, false, false><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 1: KERNEL<L, COLL, false, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 2: KERNEL<L, COLL, true, false><<<GRID, THREADS, 0, s>>>(a); break; \
+		default: KERNEL<L, COLL, true, true><<<GRID, THREADS, 0, s>>>(a); break; \
 		} \
 	} while (0)
+#define LUMA_DISPATCH(KERNEL, GRID, THREADS) \
+	do { \
+		if constexpr (L::Q == 27) { LUMA_DISPATCH_FT(KERNEL, COLL_KBC, GRID, THREADS); } \
+		else if (coll == COLL_KBC) { if constexpr (L::Q == 9) { LUMA_DISPATCH_FT(KERNEL, COLL_KBC, GRID, THREADS); } } \
+		else if (coll == COLL_SMAG) { LUMA_DISPATCH_FT(KERNEL, COLL_SMAG, GRID, THREADS); } \
+		else { LUMA_DISPATCH_FT(KERNEL, COLL_BGK, GRID, THREADS); } \
+	} while (0)
 
-template <class L> void launch_step(const StepArgs &a, bool smag, bool force, int nplanes, cudaStream_t s, int64_t *launches)
+template <class L> void launch_step(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches)
 {
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
@@ -566,73 +589,13 @@ template <class L> void launch_step(const StepArgs &a, bool smag, bool force, in
 	if (launches) ++*launches;
 }
 
-template <class L> void launch_bc(const StepArgs &a, bool smag, bool force, cudaStream_t s, int64_t *launches)
+template <class L> void launch_bc(const StepArgs &a, int coll, bool force, cudaStream_t s, int64_t *launches)
 {
 	if (a.n_bc <= 0) return;
 	const int threads = 64;
 	dim3 grid((a.n_bc + threads - 1) / threads);
 	LUMA_DISPATCH(k_bc, grid, threads);
 	if (launches) ++*launches;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Halo exchange without a communication library: the populations that leave through a slab face are
-// stored straight into the neighbour GPU's ghost plane (NVLink peer memory, mapped through CUDA IPC);
-// the last CTA to finish publishes the exchange number in the neighbours' arrival flags
-// (fence.sys + release store), and the receiver's k_halo_wait acquires it before anything reads the
-// ghost planes.  Replaces MpiManager::mpi_communicate's pack / MPI_Isend / MPI_Recv / unpack
-// (src/MpiManager.cpp:631-815) by one store per population element.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_halo_push(const HaloPushArgs a)
-{
-	const int m = blockIdx.y;
-	const double *__restrict__ src = a.src[m];
-	double *__restrict__ dst = a.dst[m];
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += (long long)gridDim.x * blockDim.x)
-		dst[i] = src[i];
-	__threadfence_system();
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		const unsigned int total = gridDim.x * gridDim.y;
-		if (atomicAdd(a.done, 1u) == total - 1)
-		{
-			*a.done = 0;
-			__threadfence_system();
-			for (int side = 0; side < 2; ++side)
-				asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a.peer_flag[side]), "l"(a.value) : "memory");
-		}
-	}
-}
-
-void launch_halo_push(const HaloPushArgs &a, cudaStream_t s)
-{
-	if (a.nmsg <= 0) return;
-	unsigned bx = (unsigned)((a.count + 255) / 256);
-	if (bx > 64) bx = 64;
-	k_halo_push<<<dim3(bx, (unsigned)a.nmsg), 256, 0, s>>>(a);
-}
-
-// thread 0 waits for the left neighbour's data, thread 1 for the right neighbour's; gives up after
-// 20 s (a dead peer must not hang the GPU) and reports it through *timed_out
-__global__ void k_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out)
-{
-	if (threadIdx.x > 1) return;
-	unsigned long long t0, t1, seen;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-	for (;;)
-	{
-		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + threadIdx.x) : "memory");
-		if (seen >= value) break;
-		__nanosleep(64);
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-		if (t1 - t0 > 20000000000ull) { *timed_out = 1; break; }
-	}
-}
-
-void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s)
-{
-	k_halo_wait<<<1, 32, 0, s>>>(flags, value, timed_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -656,7 +619,7 @@ __global__ void k_cell_words(const GeomArgs g)
 	uint32_t w = 0;
 	if (cls != CLS_SKIP)
 	{
-		w = cls << CW_CLASS_SHIFT;
+		w = cls << CW<L>::CLASS_SHIFT;
 #pragma unroll
 		for (int v = 0; v < L::Q - 1; ++v)
 		{
@@ -667,8 +630,8 @@ __global__ void k_cell_words(const GeomArgs g)
 			const long long src = ((long long)sp * g.M + sj) * g.K + sk;
 			if (g.types[src] == 0) w |= 1u << v;
 		}
-		if (j == 0 || j == g.M - 1 || (L::D == 3 && (k == 0 || k == g.K - 1))) w |= CW_EDGE;
-		if (cls >= CLS_VELOCITY && g.bcdesc) w |= g.bcdesc[id];
+		if (j == 0 || j == g.M - 1 || (L::D == 3 && (k == 0 || k == g.K - 1))) w |= CW<L>::EDGE;
+		if (L::DESC_IN_WORD && cls >= CLS_VELOCITY && g.bcdesc) w |= g.bcdesc[id];
 	}
 	g.cw[id] = w;
 }
@@ -805,39 +768,6 @@ template <class L> void launch_soa_to_aos(const double *soa, double *aos, long l
 {
 	if (n > 0) k_soa_to_aos<L::Q><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(soa, aos, stride, first, n);
 }
-void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int ncomp, long long first, long long n, cudaStream_t s)
-{
-	if (n <= 0) return;
-	if (ncomp == 6) k_aos_to_soa<6><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(aos, soa, stride, first, n);
-	else if (ncomp == 3) k_aos_to_soa<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(aos, soa, stride, first, n);
-	else k_aos_to_soa<2><<<(unsigned)((n + 63) / 64), 128, 0, s>>>(aos, soa, stride, first, n);
-}
-void launch_u_soa_to_aos(const double *soa, double *aos, long long stride, int ncomp, long long first, long long n, cudaStream_t s)
-{
-	if (n <= 0) return;
-	if (ncomp == 6) k_soa_to_aos<6><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(soa, aos, stride, first, n);
-	else if (ncomp == 3) k_soa_to_aos<3><<<(unsigned)((n + 63) / 64), 192, 0, s>>>(soa, aos, stride, first, n);
-	else k_soa_to_aos<2><<<(unsigned)((n + 63) / 64), 128, 0, s>>>(soa, aos, stride, first, n);
-}
-
-__global__ void k_types_from_i32(const int32_t *__restrict__ in, uint8_t *__restrict__ out, long long n)
-{
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = (uint8_t)in[i];
-}
-__global__ void k_types_to_i32(const uint8_t *__restrict__ in, int32_t *__restrict__ out, long long n)
-{
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = (int32_t)in[i];
-}
-void launch_types_from_i32(const int32_t *in, uint8_t *out, long long n, cudaStream_t s)
-{
-	if (n > 0) k_types_from_i32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
-}
-void launch_types_to_i32(const uint8_t *in, int32_t *out, long long n, cudaStream_t s)
-{
-	if (n > 0) k_types_to_i32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
-}
 
 // ------------------------------------------------------------------------------------------------
 // momentum exchange on eSolid sites, ObjectManager::computeLiftDrag(i,j,k,g)
@@ -908,43 +838,15 @@ template <class L> int launch_momex(const double *f_prev, const uint8_t *types, 
 	return blocks;
 }
 
-// ------------------------------------------------------------------------------------------------
-// self-test: div_const against IEEE division on pseudo-random operands (all binades the step sees)
-// ------------------------------------------------------------------------------------------------
-__global__ void k_selftest_div(const LbmConst C, unsigned long long seed, long long n, unsigned long long *mismatches)
-{
-	unsigned long long bad = 0;
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-	{
-		unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);   // splitmix64
-		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-		z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-		z ^= z >> 31;
-		const unsigned long long mant = z & 0xFFFFFFFFFFFFFull;
-		const unsigned long long expo = 1023ull - 90ull + ((z >> 52) % 100ull);                // 2^-90 .. 2^9
-		const unsigned long long sign = (z >> 63) << 63;
-		const double a = __longlong_as_double((long long)(sign | (expo << 52) | mant));
-		if (div_const(a, C.cs2, C.inv_cs2) != a / C.cs2) ++bad;
-		if (div_const(a, C.den, C.inv_den) != a / C.den) ++bad;
-	}
-	if (bad) atomicAdd(mismatches, bad);
-}
-void launch_selftest_div(const LbmConst &C, unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t s)
-{
-	k_selftest_div<<<148 * 8, 256, 0, s>>>(C, seed, n, mismatches);
-}
-
 // explicit instantiations
 #define LUMA_INST(L) \
-	template void launch_step<L>(const StepArgs &, bool, bool, int, cudaStream_t, int64_t *); \
-	template void launch_bc<L>(const StepArgs &, bool, bool, cudaStream_t, int64_t *); \
+	template void launch_step<L>(const StepArgs &, int, bool, int, cudaStream_t, int64_t *); \
+	template void launch_bc<L>(const StepArgs &, int, bool, cudaStream_t, int64_t *); \
 	template void launch_velsrc<L>(const VelSrcArgs &, cudaStream_t, int64_t *); \
 	template void launch_cell_words<L>(const GeomArgs &, cudaStream_t); \
 	template void launch_synthetic<L>(const SynthArgs &, cudaStream_t); \
 	template void launch_aos_to_soa<L>(const double *, double *, long long, long long, long long, cudaStream_t); \
 	template void launch_soa_to_aos<L>(const double *, double *, long long, long long, long long, cudaStream_t); \
 	template int launch_momex<L>(const double *, const uint8_t *, long long, int, int, int, int, int, int, int, double *, int, cudaStream_t);
-LUMA_INST(D3Q19)
-LUMA_INST(D2Q9)
 
 }  // namespace luma

@@ -17,12 +17,19 @@
 
 namespace luma {
 
-// ---- direction tables: src/stdafx.cpp:81-102 (D3Q19), :114-125 (D2Q9); rest population last;
-//      opposites are (v ^ 1) for v < Q-1 (src/GridUtils.cpp:54-55, :66-67) ----
+// ---- direction tables: src/stdafx.cpp:81-102 (D3Q19), :114-125 (D2Q9), :41-70 (D3Q27, the lattice of
+//      L_USE_KBC_COLLISION builds in 3D); rest population last; opposites are (v ^ 1) for v < Q-1
+//      (src/GridUtils.cpp:40-41, :54-55, :66-67).
+//      WREST = weight class of the rest population; DESC_IN_WORD = the wall descriptor fits the cell word
+//      beside the link bits; REGULARISABLE = L_REGULARISED_BOUNDARIES is allowed on this lattice (the
+//      reference refuses it on D3Q27, src/GridObj_init_grids.cpp:266-270) ----
 struct D3Q19
 {
 	static constexpr int Q = 19;
 	static constexpr int D = 3;
+	static constexpr int WREST = 2;
+	static constexpr bool DESC_IN_WORD = true;
+	static constexpr bool REGULARISABLE = true;
 	__host__ __device__ static constexpr int c(int v, int d)
 	{
 		constexpr int T[19][3] = {
@@ -40,6 +47,9 @@ struct D2Q9
 {
 	static constexpr int Q = 9;
 	static constexpr int D = 2;
+	static constexpr int WREST = 2;
+	static constexpr bool DESC_IN_WORD = true;
+	static constexpr bool REGULARISABLE = true;
 	__host__ __device__ static constexpr int c(int v, int d)
 	{
 		constexpr int T[9][3] = {
@@ -49,6 +59,28 @@ struct D2Q9
 	}
 	// weight class: 0 -> 1/9, 1 -> 1/36, 2 -> 4/9   (src/stdafx.cpp:147-148)
 	__host__ __device__ static constexpr int wclass(int v) { return v < 4 ? 0 : (v < 8 ? 1 : 2); }
+};
+
+struct D3Q27
+{
+	static constexpr int Q = 27;
+	static constexpr int D = 3;
+	static constexpr int WREST = 3;
+	static constexpr bool DESC_IN_WORD = false;
+	static constexpr bool REGULARISABLE = false;
+	__host__ __device__ static constexpr int c(int v, int d)
+	{
+		constexpr int T[27][3] = {
+			{ 1, 0, 0 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, -1, 0 }, { 0, 0, 1 }, { 0, 0, -1 },
+			{ 0, 1, 1 }, { 0, -1, -1 }, { 0, 1, -1 }, { 0, -1, 1 },
+			{ 1, 0, 1 }, { -1, 0, -1 }, { 1, 0, -1 }, { -1, 0, 1 },
+			{ 1, 1, 0 }, { -1, -1, 0 }, { 1, -1, 0 }, { -1, 1, 0 },
+			{ 1, 1, 1 }, { -1, -1, -1 }, { -1, -1, 1 }, { 1, 1, -1 }, { -1, 1, 1 }, { 1, -1, -1 }, { 1, -1, 1 }, { -1, 1, -1 },
+			{ 0, 0, 0 } };
+		return T[v][d];
+	}
+	// weight class: 0 -> 2/27, 1 -> 1/54, 2 -> 1/216, 3 -> 8/27   (src/stdafx.cpp:130-136)
+	__host__ __device__ static constexpr int wclass(int v) { return v < 6 ? 0 : (v < 18 ? 1 : (v < 26 ? 2 : 3)); }
 };
 
 template <class L> __host__ __device__ constexpr int opposite(int v) { return v == L::Q - 1 ? v : (v ^ 1); }
@@ -75,8 +107,8 @@ struct LbmConst
 	double inv_den;   // 1.0 / den
 	double k1;        // 1.0 - cs2   = (SQ(c) - SQ(cs)) for c = +-1
 	double k0;        // 0.0 - cs2   for c = 0
-	double w[3];      // lattice weights by class
-	double wden[3];   // w[cls] / den                                        optimised.cpp:498
+	double w[4];      // lattice weights by class
+	double wden[4];   // w[cls] / den                                        optimised.cpp:498
 };
 
 // correctly rounded a / b for the two constant divisors (y = RN(1/b)); see header comment
@@ -87,7 +119,7 @@ __device__ __forceinline__ double div_const(double a, double b, double y)
 	return fma(r, y, q);
 }
 
-// ---- cell word (one uint32 per site, built once by build_cell_words) ----
+// ---- cell word (one uint32 per site, built once by k_cell_words); D2Q9 / D3Q19 layout ----
 //  bits  0..17  link v (v < Q-1) bounces back: the site this population is pulled from is eSolid  (optimised.cpp:238)
 //  bit   18     site lies on the first/last row or column of the array (periodic wrap needed in y or z)
 //  bits 19..21  class: 0 not updated (eSolid, eRefined, non-regularised eVelocity), 1 eFluid with ordinary
@@ -97,12 +129,21 @@ __device__ __forceinline__ double div_const(double a, double b, double y)
 //  bits 22..23  normalDirection          } wall descriptor of velocity/pressure/slip sites,
 //  bits 24..29  normal vector + 1 (2b x3)} GridUtils::isWithinDomainWall, src/GridUtils.cpp:1369
 //  bits 30..31  edgeCount                }
-enum : uint32_t { CW_LINKS = 0x3FFFFu, CW_EDGE = 1u << 18, CW_CLASS_SHIFT = 19, CW_CLASS_MASK = 7u, CW_ND_SHIFT = 22, CW_N_SHIFT = 24, CW_EC_SHIFT = 30 };
+//  D3Q27 has 26 links: bits 0..25 links, 26 the first/last row or column flag, 27..29 the class; the wall
+//  descriptor (only slip sites need it there: no regularised boundaries on D3Q27) stays in the separate
+//  per-site descriptor array, with the same bit positions 22..31.
+enum : uint32_t { CW_CLASS_MASK = 7u, CW_ND_SHIFT = 22, CW_N_SHIFT = 24, CW_EC_SHIFT = 30 };
+template <class L> struct CW
+{
+	static constexpr uint32_t LINKS = (L::Q == 27) ? 0x3FFFFFFu : 0x3FFFFu;
+	static constexpr uint32_t EDGE = (L::Q == 27) ? (1u << 26) : (1u << 18);
+	static constexpr int CLASS_SHIFT = (L::Q == 27) ? 27 : 19;
+};
 enum : uint32_t { CLS_SKIP = 0, CLS_FLUID = 1, CLS_VELOCITY = 2, CLS_PRESSURE = 3, CLS_GENERAL = 4 };
 // eType, inc/Enumerations.h:84-96
 enum : uint8_t { T_SOLID = 0, T_FLUID = 1, T_REFINED = 2, T_VELOCITY = 6, T_PRESSURE = 7, T_SLIP = 8, T_EXTRAPOLATE_RIGHT = 9 };
 
-__host__ __device__ inline uint32_t cw_class(uint32_t w) { return (w >> CW_CLASS_SHIFT) & CW_CLASS_MASK; }
+template <class L> __host__ __device__ inline uint32_t cw_class(uint32_t w) { return (w >> CW<L>::CLASS_SHIFT) & CW_CLASS_MASK; }
 __host__ __device__ inline uint32_t cw_pack_bc(int ec, int nd, int nx, int ny, int nz)
 {
 	return ((uint32_t)(ec & 3) << CW_EC_SHIFT) | ((uint32_t)(nd & 3) << CW_ND_SHIFT) |
@@ -127,9 +168,9 @@ __device__ __forceinline__ void equilibrium_all(const double rho, const double (
 	const double x01 = (2.0 * u[0]) * u[1];
 	const double x02 = (L::D == 3) ? (2.0 * u[0]) * u[2] : 0.0;
 	const double x12 = (L::D == 3) ? (2.0 * u[1]) * u[2] : 0.0;
-	double rw[3];
+	double rw[4];
 #pragma unroll
-	for (int k = 0; k < 3; ++k) rw[k] = rho * C.w[k];
+	for (int k = 0; k <= L::WREST; ++k) rw[k] = rho * C.w[k];
 
 #pragma unroll
 	for (int v = 0; v < L::Q - 1; v += 2)
@@ -155,7 +196,7 @@ __device__ __forceinline__ void equilibrium_all(const double rho, const double (
 		double B = t0[0] + t0[1];
 		if (L::D == 3) B = B + t0[2];
 		const double qb = div_const(B, C.den, C.inv_den);
-		feq[L::Q - 1] = rw[2] * (1.0 + qb);
+		feq[L::Q - 1] = rw[L::WREST] * (1.0 + qb);
 	}
 }
 
@@ -239,7 +280,7 @@ __device__ __forceinline__ double smagorinsky_omega(const double (&f)[L::Q], con
 
 // ---- Guo forcing term of one direction, GridObj::_LBM_forceGrid_opt (optimised.cpp:959-989) ----
 template <class L>
-__device__ __forceinline__ double guo_force(const int v, const double (&u)[3], const double (&F)[3], const LbmConst &C, const double (&lam)[3])
+__device__ __forceinline__ double guo_force(const int v, const double (&u)[3], const double (&F)[3], const LbmConst &C, const double (&lam)[4])
 {
 	double beta = 0.0;
 #pragma unroll
@@ -249,6 +290,109 @@ __device__ __forceinline__ double guo_force(const int v, const double (&u)[3], c
 #pragma unroll
 	for (int d = 0; d < L::D; ++d) fi = fi + F[d] * ((double)L::c(v, d) * (1.0 + beta) - u[d]);
 	return fi * lam[L::wclass(v)];
+}
+
+// ---- KBC collision, GridObj::_LBM_kbcCollide_opt (optimised.cpp:1122-1305): KBC-D on D2Q9, KBC-N4 on
+//      D3Q27.  `fo` are the populations the reference reads there: `f`, the PREVIOUS time level at this
+//      very site (:1150, :1292) -- not the streamed fNew, which only feeds rho and u.  Moment order
+//      (:1153-1176): 2-D xx, xy, yy; 3-D xx, xxy, xxz, xy, xyy, xyz, xz, xzz, yy, yyz, yz, yzz, zz. ----
+template <class L> __host__ __device__ constexpr int kbc_coef(int v, int m)
+{
+	constexpr int T3[13][3] = { { 0, 0, -1 }, { 0, 0, 1 }, { 0, 0, 2 }, { 0, 1, -1 }, { 0, 1, 1 }, { 0, 1, 2 }, { 0, 2, -1 },
+		{ 0, 2, 2 }, { 1, 1, -1 }, { 1, 1, 2 }, { 1, 2, -1 }, { 1, 2, 2 }, { 2, 2, -1 } };
+	constexpr int T2[3][3] = { { 0, 0, -1 }, { 0, 1, -1 }, { 1, 1, -1 } };
+	const int a = (L::D == 3) ? T3[m][0] : T2[m][0], b = (L::D == 3) ? T3[m][1] : T2[m][1], t = (L::D == 3) ? T3[m][2] : T2[m][2];
+	return L::c(v, a) * L::c(v, b) * (t < 0 ? 1 : L::c(v, t));
+}
+
+template <class L, bool FORCE>
+__device__ __forceinline__ void kbc_collide(const double (&u)[3], const double (&feq)[L::Q], const double (&fo)[L::Q],
+	const double beta_m1, const double inv_beta, const double (&F)[3], const LbmConst &C, const double (&lam)[4], double (&out)[L::Q])
+{
+	constexpr int NM = (L::D == 3) ? 13 : 3;
+	double M[NM], fneq[L::Q], ds[L::Q], dh[L::Q];
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v) fneq[v] = fo[v] - feq[v];
+#pragma unroll
+	for (int m = 0; m < NM; ++m)
+	{
+		double acc = 0.0;
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v)
+		{
+			const int cf = kbc_coef<L>(v, m);
+			if (cf != 0) acc = acc + ((cf > 0) ? fneq[v] : -fneq[v]);
+		}
+		M[m] = acc;
+	}
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		const int c0 = L::c(v, 0), c1 = L::c(v, 1), c2 = L::c(v, 2);
+		double d;
+		if constexpr (L::D == 3)
+		{
+			// index 0 xx, 1 xxy, 2 xxz, 3 xy, 4 xyy, 5 xyz, 6 xz, 7 xzz, 8 yy, 9 yyz, 10 yz, 11 yzz, 12 zz
+			const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6],
+				m7 = M[7], m8 = M[8], m9 = M[9], m10 = M[10], m11 = M[11], m12 = M[12];
+			if (c0 == 0)
+			{
+				if (c1 == 0)
+				{
+					if (c2 == 0) d = (-(m0 + m8 + m12));
+					else d = ((-(m0 - m12) - (m8 - m12)) / 6.0 + (m0 + m8 + m12) / 6.0 - (double)c2 * 0.5 * (m2 + m9));
+				}
+				else
+				{
+					if (c2 == 0) d = ((-(m0 - m12) + 2.0 * (m8 - m12)) / 6.0 + (m0 + m8 + m12) / 6.0 - (double)c1 * 0.5 * (m1 + m11));
+					else d = ((double)(c1 * c2) * 0.25 * m10 + ((double)c2 * 0.25 * m9 + (double)c1 * 0.25 * m11));
+				}
+			}
+			else
+			{
+				if (c1 == 0)
+				{
+					if (c2 == 0) d = ((2.0 * (m0 - m12) - (m8 - m12)) / 6.0 + (m0 + m8 + m12) / 6.0 - (double)c0 * 0.5 * (m4 + m7));
+					else d = ((double)(c0 * c2) * 0.25 * m6 + ((double)c2 * 0.25 * m2 + (double)c0 * 0.25 * m7));
+				}
+				else
+				{
+					if (c2 == 0) d = ((double)(c0 * c1) * 0.25 * m3 + ((double)c1 * 0.25 * m1 + (double)c0 * 0.25 * m4));
+					else d = ((double)(c0 * c1 * c2) * m5 / 8.0);
+				}
+			}
+		}
+		else
+		{
+			if (c0 == 0)
+			{
+				if (c1 == 0) d = 0.0;
+				else d = -0.25 * (M[0] - M[2]);
+			}
+			else
+			{
+				if (c1 == 0) d = 0.25 * (M[0] - M[2]);
+				else d = 0.25 * (double)(c0 * c1) * M[1];
+			}
+		}
+		ds[v] = d;
+		dh[v] = fneq[v] - d;
+	}
+	double top = 0.0, bot = 0.0;
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		top = top + ds[v] * dh[v] / feq[v];
+		bot = bot + dh[v] * dh[v] / feq[v];
+	}
+	double gamma = 2.0;
+	if (!(bot == 0.0)) gamma = beta_m1 - (2.0 - beta_m1) * (top / bot);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		if (FORCE) out[v] = fo[v] - inv_beta * (2.0 * ds[v] + gamma * dh[v]) + guo_force<L>(v, u, F, C, lam);
+		else out[v] = fo[v] - inv_beta * (2.0 * ds[v] + gamma * dh[v]);
+	}
 }
 
 }  // namespace luma

@@ -51,6 +51,7 @@ class Definitions:
     L_NU: Optional[float] = None              # if set, overrides L_RE (init_grids.cpp:336-340)
     # --- models (definitions.h:112-128) ---
     L_USE_BGKSMAG: bool = False
+    L_USE_KBC_COLLISION: bool = False         # KBC-D on D2Q9 / KBC-N4 on D3Q27 instead of LBGK (definitions.h:125)
     L_CSMAG: float = 0.3
     L_GRAVITY_ON: bool = False
     L_GRAVITY_FORCE: float = 0.0
@@ -90,7 +91,9 @@ class Definitions:
 
     @property
     def L_NUM_VELS(self) -> int:
-        return 19 if self.L_DIMS == 3 else 9               # definitions.h:299-309 (no KBC on this path)
+        if self.L_DIMS == 3:
+            return 27 if self.L_USE_KBC_COLLISION else 19  # definitions.h:299-310
+        return 9
 
     @property
     def dh(self) -> float:

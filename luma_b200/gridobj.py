@@ -48,6 +48,7 @@ class GridObj:
         p.re = float(defs.L_RE) if defs.L_RE is not None else 1.0
         p.t = t
         p.time_averaged = int(defs.L_COMPUTE_TIME_AVERAGED_QUANTITIES)
+        p.kbc = int(defs.L_USE_KBC_COLLISION)
         self.params = p
         self.rank, self.nranks = rank, nranks
         self.x_offset, self.x_count = p.x_offset, p.x_count

@@ -113,8 +113,11 @@ void GridObj::LBM_multi_opt(int subcycle)
 #ifdef L_COMPUTE_TIME_AVERAGED_QUANTITIES
 		p.time_averaged = 1;
 #endif
-#if defined(L_USE_KBC_COLLISION) || defined(L_IBM_ON) || (L_NUM_LEVELS != 0)
-		L_ERROR("luma_b200: KBC, IBM and grid refinement are outside the accelerated path", GridUtils::logfile);
+#ifdef L_USE_KBC_COLLISION
+		p.kbc = 1;      /* _LBM_kbcCollide_opt instead of _LBM_collide_opt; L_NUM_VELS is 27 in 3-D */
+#endif
+#if defined(L_IBM_ON) || (L_NUM_LEVELS != 0)
+		L_ERROR("luma_b200: IBM and grid refinement are outside the accelerated path", GridUtils::logfile);
 #endif
 		check(luma_b200_create(&g_dev, &p), "create");
 #ifdef L_BUILD_FOR_MPI

@@ -13,8 +13,9 @@
  * Switch-type macros (L_GRAVITY_ON, L_USE_BGKSMAG, L_REGULARISED_BOUNDARIES,
  * L_NO_FLOW, L_VELOCITY_RAMP, L_REYNOLDS_RAMP, L_ENABLE_OPENMP, L_LD_OUT, ...)
  * are simply defined, or not, by the case header.  The build never defines
- * L_BUILD_FOR_MPI, L_IBM_ON, L_HDF5_OUTPUT, L_GEOMETRY_FILE or
- * L_USE_KBC_COLLISION: those subsystems are outside the hot path.
+ * L_BUILD_FOR_MPI, L_IBM_ON, L_HDF5_OUTPUT or L_GEOMETRY_FILE: those
+ * subsystems are outside the hot path.  L_USE_KBC_COLLISION is a
+ * case switch (last row).
  */
 #ifndef LBM_DEFINITIONS_H
 #define LBM_DEFINITIONS_H
@@ -159,7 +160,11 @@ const static double cProbeLimsZ[2] = { L_PROBE_MIN_Z, L_PROBE_MAX_Z };
 
 /* ---- dependent options (definitions.h:299-337) ---- */
 #if (L_DIMS == 3)
+#ifdef L_USE_KBC_COLLISION
+#define L_NUM_VELS 27
+#else
 #define L_NUM_VELS 19
+#endif
 #define L_MPI_DIRS 26
 #else
 #define L_NUM_VELS 9

@@ -1,6 +1,6 @@
 /* TEST INFRASTRUCTURE ONLY -- see luma_oracle.h.  Plain-C (gcc, no FMA contraction, no fast-math)
  * restatement of LUMA v1.7.12's level-0 time step, GridObj::LBM_multi_opt, for a serial build
- * without refinement, IBM, BFL, KBC or MPI.  Paths below are under /root/reference/LUMA/.
+ * without refinement, IBM, BFL or MPI.  Paths below are under /root/reference/LUMA/.
  *
  * The restatement keeps the reference's memory layout (AoS, inc/IVector.h:94-134), loop order
  * (i, j, k; v ascending) and the left-to-right order of every floating-point expression, because
@@ -23,22 +23,27 @@ enum { eSolid = 0, eFluid = 1, eRefined = 2, eVelocity = 6, ePressure = 7, eSlip
 static const int C19[19][3] = {
 	{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1},{1,1,0},{-1,-1,0},{1,-1,0},{-1,1,0},
 	{0,1,1},{0,-1,-1},{0,1,-1},{0,-1,1},{1,0,1},{-1,0,-1},{-1,0,1},{1,0,-1},{0,0,0} };
+/* D3Q27 (L_USE_KBC_COLLISION in 3D), src/stdafx.cpp:41-70 */
+static const int C27[27][3] = {
+	{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1},{0,1,1},{0,-1,-1},{0,1,-1},{0,-1,1},
+	{1,0,1},{-1,0,-1},{1,0,-1},{-1,0,1},{1,1,0},{-1,-1,0},{1,-1,0},{-1,1,0},
+	{1,1,1},{-1,-1,-1},{-1,-1,1},{1,1,-1},{-1,1,1},{1,-1,-1},{1,-1,1},{-1,1,-1},{0,0,0} };
 static const int C9[9][3] = {
 	{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{1,1,0},{-1,-1,0},{1,-1,0},{-1,1,0},{0,0,0} };
 
 struct OracleGrid {
 	OracleCase cs_;            /* the case */
 	int D, Q, N, M, K;
-	int c[19][3];
-	int opp[19];               /* GridUtils::dir_opposites, src/GridUtils.cpp:54-55,:66-67 */
-	double w[19];              /* src/stdafx.cpp:140-148 */
+	int c[27][3];
+	int opp[27];               /* GridUtils::dir_opposites, src/GridUtils.cpp:40-41,:54-55,:66-67 */
+	double w[27];              /* src/stdafx.cpp:130-148 */
 	double cs;                 /* src/stdafx.cpp:153 */
 	double dh, dt, nu, omega, gravity, uref, rho_out;
 	double Lx, Ly, Lz;         /* GridManager::global_edges[e?Max][0], src/GridManager.cpp:45-51 */
 	int t;
 	double *xpos, *ypos, *zpos;
 	double *uin[3];
-	int reflect[3][19];        /* GridUtils::dir_reflect, src/GridUtils.cpp:46-51,:60-64 */
+	int reflect[3][27];        /* GridUtils::dir_reflect, src/GridUtils.cpp:46-51,:60-64 */
 	double *f, *fnew, *rho, *u, *force_xyz, *force_i;
 	double *rho_timeav, *ui_timeav, *uiuj_timeav;   /* inc/GridObj.h:93-95, src/GridObj_init_grids.cpp:304-306 */
 	int32_t *lattyp, *wall;
@@ -398,7 +403,7 @@ static double smag_omega(const OracleGrid *g, size_t id, double omega)
 	const int Q = g->Q, D = g->D;
 	const double cs = g->cs;
 	double S[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
-	double fneq[19];
+	double fneq[27];
 	for (int v = 0; v < Q; ++v) fneq[v] = g->fnew[v + id * Q] - feq_at(g, id, v);
 	for (int a = 0; a < D; ++a)
 		for (int b = a; b < D; ++b)
@@ -431,6 +436,104 @@ static void collide_site(OracleGrid *g, size_t id)
 			g->fnew[v + id * Q] += omega_s * (feq_at(g, id, v) - g->fnew[v + id * Q]) + g->force_i[v + id * Q];
 		else
 			g->fnew[v + id * Q] += omega_s * (feq_at(g, id, v) - g->fnew[v + id * Q]);
+	}
+}
+
+/* GridObj::_LBM_kbcCollide_opt, src/GridObj_ops_lbm_optimised.cpp:1122-1305 (KBC-D on D2Q9, KBC-N4 on
+ * D3Q27).  NB the reference reads `f` -- the lattice of the PREVIOUS time level at this site, not the
+ * streamed `fNew` (:1150, :1292) -- so the streamed (and regularised) populations only reach rho and u. */
+static void kbc_collide_site(OracleGrid *g, size_t id)
+{
+	const int Q = g->Q, D = g->D;
+	const int nm = (D == 3) ? 13 : 3;
+	double ds[27], dh[27], fneq[27], feq[27], Mneq[13];
+	int C[13 * 27];
+	double gamma;
+	for (int m = 0; m < nm; ++m) Mneq[m] = 0.0;
+	for (int m = 0; m < nm * Q; ++m) C[m] = 1;
+	for (int v = 0; v < Q; ++v)
+	{
+		feq[v] = feq_at(g, id, v);
+		fneq[v] = g->f[v + id * Q] - feq[v];
+		int idx = 0;
+		for (int sig = 0; sig < D; ++sig)
+			for (int gam = sig; gam < D; ++gam)
+			{
+				C[idx + v * nm] = g->c[v][sig] * g->c[v][gam];
+				Mneq[idx] += fneq[v] * C[idx + v * nm];
+				idx++;
+				if (D == 3)
+					for (int del = gam; del < D; ++del)
+						if (sig != gam || gam != del || sig != del)
+						{
+							C[idx + v * nm] = g->c[v][sig] * g->c[v][gam] * g->c[v][del];
+							Mneq[idx] += fneq[v] * C[idx + v * nm];
+							idx++;
+						}
+			}
+	}
+	for (int v = 0; v < Q; ++v)
+	{
+		const int *c = g->c[v];
+		if (D == 3)
+		{
+			if (c[0] == 0)
+			{
+				if (c[1] == 0)
+				{
+					if (c[2] == 0) ds[v] = (-(Mneq[0] + Mneq[8] + Mneq[12]));
+					else ds[v] = ((-(Mneq[0] - Mneq[12]) - (Mneq[8] - Mneq[12])) / 6.0 + (Mneq[0] + Mneq[8] + Mneq[12]) / 6.0 - c[2] * 0.5 * (Mneq[2] + Mneq[9]));
+				}
+				else
+				{
+					if (c[2] == 0) ds[v] = ((-(Mneq[0] - Mneq[12]) + 2.0 * (Mneq[8] - Mneq[12])) / 6.0 + (Mneq[0] + Mneq[8] + Mneq[12]) / 6.0 - c[1] * 0.5 * (Mneq[1] + Mneq[11]));
+					else ds[v] = (C[10 + v * nm] * 0.25 * Mneq[10] + (c[2] * 0.25 * Mneq[9] + c[1] * 0.25 * Mneq[11]));
+				}
+			}
+			else
+			{
+				if (c[1] == 0)
+				{
+					if (c[2] == 0) ds[v] = ((2.0 * (Mneq[0] - Mneq[12]) - (Mneq[8] - Mneq[12])) / 6.0 + (Mneq[0] + Mneq[8] + Mneq[12]) / 6.0 - c[0] * 0.5 * (Mneq[4] + Mneq[7]));
+					else ds[v] = (C[6 + v * nm] * 0.25 * Mneq[6] + (c[2] * 0.25 * Mneq[2] + c[0] * 0.25 * Mneq[7]));
+				}
+				else
+				{
+					if (c[2] == 0) ds[v] = (C[3 + v * nm] * 0.25 * Mneq[3] + (c[1] * 0.25 * Mneq[1] + c[0] * 0.25 * Mneq[4]));
+					else ds[v] = (C[5 + v * nm] * Mneq[5] / 8.0);
+				}
+			}
+		}
+		else
+		{
+			if (c[0] == 0)
+			{
+				if (c[1] == 0) ds[v] = 0.0;
+				else ds[v] = -0.25 * (Mneq[0] - Mneq[2]);
+			}
+			else
+			{
+				if (c[1] == 0) ds[v] = 0.25 * (Mneq[0] - Mneq[2]);
+				else ds[v] = 0.25 * C[1 + v * nm] * Mneq[1];
+			}
+		}
+		dh[v] = fneq[v] - ds[v];
+	}
+	double top_prod = 0.0, bot_prod = 0.0;
+	for (int v = 0; v < Q; ++v)
+	{
+		top_prod += ds[v] * dh[v] / feq[v];
+		bot_prod += dh[v] * dh[v] / feq[v];
+	}
+	double beta_m1 = 2.0 / g->omega;
+	if (bot_prod == 0.0) gamma = 2.0;
+	else gamma = beta_m1 - (2.0 - beta_m1) * (top_prod / bot_prod);
+	for (int v = 0; v < Q; ++v)
+	{
+		if (g->cs_.gravity_on)
+			g->fnew[v + id * Q] = g->f[v + id * Q] - (1.0 / beta_m1) * (2.0 * ds[v] + gamma * dh[v]) + g->force_i[v + id * Q];
+		else
+			g->fnew[v + id * Q] = g->f[v + id * Q] - (1.0 / beta_m1) * (2.0 * ds[v] + gamma * dh[v]);
 	}
 }
 
@@ -481,7 +584,8 @@ static void multi_opt(OracleGrid *g)
 					regularised_site(g, i, j, k, id, type);
 				macro_site(g, id, type);
 				if (c->gravity_on) force_site(g, id);
-				collide_site(g, id);
+				if (c->kbc) kbc_collide_site(g, id);   /* :147-151 */
+				else collide_site(g, id);
 			}
 	double *tmp = g->f; g->f = g->fnew; g->fnew = tmp;   /* f.swap(fNew) :159 */
 	++g->t;
@@ -500,11 +604,12 @@ OracleGrid *luma_oracle_create(const OracleCase *c)
 	OracleGrid *g = (OracleGrid *)calloc(1, sizeof(OracleGrid));
 	if (!g) return NULL;
 	g->cs_ = *c;
-	g->D = c->dims; g->Q = (c->dims == 3) ? 19 : 9;
+	g->D = c->dims; g->Q = (c->dims == 3) ? (c->kbc ? 27 : 19) : 9;   /* definitions.h:299-310 */
+	if (c->kbc && c->dims == 3 && c->regularised) { free(g); return NULL; }   /* L_ERROR, src/GridObj_init_grids.cpp:266-270 */
 	g->N = c->N; g->M = c->M; g->K = (c->dims == 3) ? c->K : 1;
 	const int Q = g->Q, D = g->D;
 	for (int v = 0; v < Q; ++v)
-		for (int d = 0; d < 3; ++d) g->c[v][d] = (D == 3) ? C19[v][d] : C9[v][d];
+		for (int d = 0; d < 3; ++d) g->c[v][d] = (D == 3) ? (Q == 27 ? C27[v][d] : C19[v][d]) : C9[v][d];
 	for (int v = 0; v < Q - 1; ++v) g->opp[v] = v ^ 1;
 	g->opp[Q - 1] = Q - 1;
 	/* dir_reflect[plane][v]: the direction with component `plane` negated */
@@ -516,7 +621,14 @@ OracleGrid *luma_oracle_create(const OracleCase *c)
 				for (int e = 0; e < 3; ++e) same = same && (g->c[r][e] == ((e == d) ? -g->c[v][e] : g->c[v][e]));
 				if (same) g->reflect[d][v] = r;
 			}
-	if (D == 3)
+	if (Q == 27)
+	{
+		for (int v = 0; v < 6; ++v) g->w[v] = 2.0 / 27.0;
+		for (int v = 6; v < 18; ++v) g->w[v] = 1.0 / 54.0;
+		for (int v = 18; v < 26; ++v) g->w[v] = 1.0 / 216.0;
+		g->w[26] = 8.0 / 27.0;
+	}
+	else if (D == 3)
 	{
 		for (int v = 0; v < 6; ++v) g->w[v] = 1.0 / 18.0;
 		for (int v = 6; v < 18; ++v) g->w[v] = 1.0 / 36.0;

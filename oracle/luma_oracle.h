@@ -47,6 +47,7 @@ typedef struct OracleCase {
 	int32_t has_box;            /* bounce-back body given as an index box */
 	int32_t box[6];             /* i0,i1,j0,j1,k0,k1 (half-open) */
 	int32_t time_averaged;      /* L_COMPUTE_TIME_AVERAGED_QUANTITIES */
+	int32_t kbc;                /* L_USE_KBC_COLLISION (D2Q9: KBC-D; 3D: D3Q27 + KBC-N4) */
 } OracleCase;
 
 typedef struct OracleGrid OracleGrid;

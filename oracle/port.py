@@ -38,7 +38,7 @@ class OracleCase(C.Structure):
         ("reynolds_ramp_on", C.c_int32), ("reynolds_ramp", C.c_double),
         ("parabolic_inlet", C.c_int32), ("pressure_delta", C.c_double),
         ("ld_out", C.c_int32), ("has_box", C.c_int32), ("box", C.c_int32 * 6),
-        ("time_averaged", C.c_int32),
+        ("time_averaged", C.c_int32), ("kbc", C.c_int32),
     ]
 
 
@@ -73,6 +73,8 @@ def case_struct(case: Case, struct_type=OracleCase):
         for a in range(6):
             s.box[a] = case.box[a]
     s.time_averaged = int(case.time_averaged)
+    if hasattr(s, "kbc"):
+        s.kbc = int(case.kbc)
     return s
 
 

@@ -22,7 +22,8 @@ def _digest(path):
     return hashlib.sha256(np.fromfile(path, dtype=np.float64).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("name", ["cav2d_64", "cyl3d", "chan3d", "tunnel2d", "cav2d_reramp", "sliptunnel2d", "fevel2d_tav", "pleft3d_tav"])
+@pytest.mark.parametrize("name", ["cav2d_64", "cyl3d", "chan3d", "tunnel2d", "cav2d_reramp", "sliptunnel2d", "fevel2d_tav", "pleft3d_tav",
+                                  "kbc2d_cyl", "kbc3d_chan"])
 def test_luma_host_with_gpu_time_step_reproduces_reference_digests(name):
     exe = os.path.join(REF, "luma_dropin_" + name)
     if not os.path.exists(exe):

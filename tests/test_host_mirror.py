@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(names) >= 18
     for nm in names:
         assert hasattr(L, nm), "symbol %s declared in include/luma_b200.h is not exported" % nm
-    assert L.luma_b200_abi_version() == 2
+    assert L.luma_b200_abi_version() == 3
 
 
 def test_struct_layout_matches_header():
@@ -70,9 +70,14 @@ def test_create_rejects_inconsistent_cases_before_touching_cuda():
     h = C.c_void_p()
     p = capi.default_params()
     p.N, p.M, p.K, p.x_count = 8, 8, 8, 8
-    p.num_vels = 27                      # KBC / D3Q27 is outside the path
-    assert L.luma_b200_create(C.byref(h), C.byref(p)) == capi.EUNSUPPORTED
-    p.num_vels = 19
+    p.num_vels = 27                      # D3Q27 only together with L_USE_KBC_COLLISION (definitions.h:299-310) ...
+    assert L.luma_b200_create(C.byref(h), C.byref(p)) == capi.EINVAL
+    p.kbc = 1                            # ... and never with regularised boundaries (init_grids.cpp:266-270)
+    assert p.regularised == 1
+    assert L.luma_b200_create(C.byref(h), C.byref(p)) == capi.EINVAL
+    p.num_vels = 19                      # KBC in 3-D means D3Q27
+    assert L.luma_b200_create(C.byref(h), C.byref(p)) == capi.EINVAL
+    p.kbc = 0
     p.omega = 2.5                        # init_grids.cpp:353-356
     assert L.luma_b200_create(C.byref(h), C.byref(p)) == capi.EINVAL
     p.omega = 1.0

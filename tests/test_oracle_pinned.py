@@ -69,7 +69,8 @@ def test_port_matches_golden_digests(name):
     g.close()
 
 
-@pytest.mark.parametrize("name", ["cav2d_64", "chan3d_gz", "tunnel3d", "cyl2d", "sliptunnel3d", "fevel2d", "fevel2d_tav", "pleft3d_tav"])
+@pytest.mark.parametrize("name", ["cav2d_64", "chan3d_gz", "tunnel3d", "cyl2d", "sliptunnel3d", "fevel2d", "fevel2d_tav", "pleft3d_tav",
+                                  "kbc2d_cyl", "kbc3d_chan"])
 def test_port_matches_compiled_reference_arrays(name):
     if port.ref_binary(name) is None:
         pytest.skip("oracle/_ref/luma_ref_%s not built here" % name)

@@ -12,7 +12,7 @@ def defs_from_case(case: Case) -> Definitions:
         L_BX=case.bx, L_BY=case.by, L_BZ=case.bz,
         L_UX0=case.ux0, L_UY0=case.uy0, L_UZ0=case.uz0,
         L_RE=case.re, L_NU=case.nu,
-        L_USE_BGKSMAG=case.bgksmag, L_CSMAG=case.csmag,
+        L_USE_BGKSMAG=case.bgksmag, L_USE_KBC_COLLISION=case.kbc, L_CSMAG=case.csmag,
         L_GRAVITY_ON=case.gravity_on, L_GRAVITY_FORCE=case.gravity_force, L_GRAVITY_DIRECTION=case.gravity_dir,
         L_NO_FLOW=case.no_flow, L_PARABOLIC_INLET=case.parabolic_inlet,
         L_WALL_LEFT=case.walls[0], L_WALL_RIGHT=case.walls[1], L_WALL_BOTTOM=case.walls[2],
