@@ -50,11 +50,12 @@ def emit(line: dict) -> None:
 
 METRIC = "MLUPS (D3Q19 fp64)"
 UNIT = "MLUPS"
-BYTES_PER_LUP = 304.0          # 19 populations x 8 B read + 19 x 8 B written (two-lattice pull), DESIGN.md
+BYTES_PER_LUP = 304.0          # D3Q19: 19 populations x 8 B read + 19 x 8 B written (two-lattice pull), DESIGN.md;
+                               # main_ours() recomputes it from the workload's lattice and collision operator
 OUT_FREQ = 100                 # L_GRID_OUT_FREQ used by the e2e leg
 
 
-WEAK = ("c2", "c5")            # cells per GPU fixed; c3 / c4 have a fixed global grid (strong scaling)
+WEAK = ("c2", "c5", "k27")     # cells per GPU fixed; c3 / c4 have a fixed global grid (strong scaling)
 
 
 RES_OVERRIDE = None            # --res: cells per GPU edge of the cavity workloads (studies only; the default is the named size)
@@ -83,6 +84,16 @@ def workload_defs(name: str, ngpus: int):
             L_WALL_LEFT=luma_b200.eVelocity, L_WALL_RIGHT=luma_b200.ePressure, L_WALL_FRONT=luma_b200.eFluid,
             L_WALL_BACK=luma_b200.eFluid, L_WALL_THICKNESS_CELLS=(1, 1, 1, 1, 0, 0),
             body_box=(256, 288, 112, 144, 0, 256))
+    if name == "k27":
+        # SURVEY 8(f-4) KBC row: periodic channel on D3Q27 with the KBC-N4 operator (non-regularised, as the reference
+        # demands on D3Q27), bounce-back walls in y, Guo forcing; 256^3 per GPU
+        res = RES_OVERRIDE or 256
+        return luma_b200.Definitions(
+            L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_BX=float(ngpus), L_BY=1.0, L_BZ=1.0,
+            L_RE=None, L_NU=2.0 / res, L_NO_FLOW=True, L_USE_KBC_COLLISION=True, L_REGULARISED_BOUNDARIES=False,
+            L_WALL_LEFT=luma_b200.eFluid, L_WALL_RIGHT=luma_b200.eFluid, L_WALL_FRONT=luma_b200.eFluid,
+            L_WALL_BACK=luma_b200.eFluid, L_WALL_THICKNESS_CELLS=(0, 0, 1, 1, 0, 0),
+            L_GRAVITY_ON=True, L_GRAVITY_FORCE=0.0158, L_GRAVITY_DIRECTION=0)
     res = RES_OVERRIDE or {"c2": 256, "c5": 384}[name]
     return luma_b200.Definitions(
         L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_BX=float(ngpus), L_BY=1.0, L_BZ=1.0,
@@ -95,6 +106,10 @@ def workload_name(name: str, ngpus: int) -> str:
     if name == "c4":
         return ("BASELINE configs[3]: flow past a square cylinder D3Q19, velocity inlet / pressure outlet, Smagorinsky LES, "
                 "1024x256x256 cells over %d x-slab(s)" % ngpus)
+    if name == "k27":
+        res = RES_OVERRIDE or 256
+        return ("SURVEY 8(f-4): periodic channel on D3Q27 with the KBC-N4 collision operator, bounce-back walls, Guo forcing, "
+                "%dx%dx%d cells (%d^3 per GPU, x-slabs)" % (res * ngpus, res, res, res))
     res = RES_OVERRIDE or {"c2": 256, "c5": 384}[name]
     base = {"c2": "BASELINE configs[1]: 3D lid-driven cavity D3Q19 BGK Re=1000",
             "c5": "BASELINE configs[4]: weak-scaling cavity D3Q19 BGK"}[name]
@@ -251,14 +266,46 @@ def main_ours(args):
         return float(t.item())
 
     defs = workload_defs(args.workload, world)
+    Q = defs.L_NUM_VELS
+    # algorithmic bytes per lattice update: Q populations read + Q written (two-lattice pull).  The KBC operator also
+    # loads the Q populations of the site itself (optimised.cpp:1150), but those are the very values a neighbouring
+    # thread pulls, so they come from L1/L2 and DRAM still moves each population once (ncu: DESIGN.md section 4)
+    BYTES_PER_LUP = 8.0 * Q * 2
     g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
     halo = "none (single GPU)"
     if world > 1:
-        halo = "NCCL send/recv of the 5 outgoing populations per face"
+        nface = {9: 3, 19: 5, 27: 9}[Q]
+        halo = "NCCL send/recv of the %d outgoing populations per face" % nface
         if args.halo == "p2p":
             from luma_b200 import ring
-            ring.attach_p2p(dist, g, rank, world)
-            halo = "device-initiated: the 5 outgoing populations per face stored into the neighbour's ghost plane over NVLink (CUDA IPC), arrival flags"
+            # peer stores need CUDA IPC peer mappings between ring neighbours; where a box cannot provide them every rank
+            # falls back to the NCCL exchange together (same kernels, same results: tests/test_gpu_multi.py)
+            ok = 1
+            try:
+                blob = g.p2p_export()
+            except Exception:
+                blob, ok = b"", 0
+            blobs = [None] * world
+            dist.all_gather_object(blobs, blob)
+            if ok and all(len(b) == 256 for b in blobs):
+                try:
+                    g.p2p_attach(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+                except Exception as ex:
+                    sys.stderr.write("rank %d: p2p_attach failed (%r)\n" % (rank, ex))
+                    ok = 0
+            else:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                halo = ("device-initiated: the %d outgoing populations per face stored into the neighbour's ghost plane over "
+                        "NVLink (CUDA IPC), arrival flags" % nface)
+            else:
+                # a handle cannot be detached: start over without peer mappings
+                g.close()
+                uid = ring.broadcast_unique_id(dist, rank)
+                g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
+                halo += " (peer mapping unavailable on this box)"
     g.LBM_initGrid()
     cells_local = g.x_count * g.M_lim * g.K_lim
     cells_global = defs.L_N * defs.L_M * defs.L_K
@@ -311,7 +358,7 @@ def main_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_step<D3Q19>", "bytes_per_lup": BYTES_PER_LUP,
+                "traffic": traffic, "kernel": "k_step<D%dQ%d>" % (defs.L_DIMS, Q), "bytes_per_lup": BYTES_PER_LUP,
                 "kernel_ms_avg": k_ms, "kernel_launches_timed": st["step_kernel_launches"], "peak_source": peak_src}
 
     # ---- end to end through the reference-facing API with host buffers ----
@@ -353,8 +400,8 @@ def main_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, world), "cells_per_gpu": cells_local,
                        "omega": g.omega, "parallelism": "x-slab x%d; halo exchange: %s" % (world, halo),
-                       "l2": "inputs larger than L2 (2 lattices x %.2f GB per GPU)" % (cells_local * 19 * 8 / 1e9),
-                       "kernel_variant": "k_step<D3Q19,%s,%s>" % ("Smagorinsky" if defs.L_USE_BGKSMAG else "BGK",
+                       "l2": "inputs larger than L2 (2 lattices x %.2f GB per GPU)" % (cells_local * Q * 8 / 1e9),
+                       "kernel_variant": "k_step<D3Q%d,%s,%s>" % (Q, "KBC" if defs.L_USE_KBC_COLLISION else ("Smagorinsky" if defs.L_USE_BGKSMAG else "BGK"),
                                                                    "Guo force" if defs.L_GRAVITY_ON else "no force"),
                        "arithmetic": "bit-identical to the reference CPU build (tests/test_gpu_parity.py)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -374,7 +421,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5"], default="c2")
+    ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5", "k27"], default="c2")
     ap.add_argument("--halo", choices=["p2p", "nccl"], default="p2p", help="multi-GPU halo exchange: peer stores (default) or NCCL send/recv")
     ap.add_argument("--res", type=int, default=None, help="cavity edge per GPU for c2/c5 (scaling studies; not the named config)")
     ap.add_argument("--no-e2e", action="store_true")

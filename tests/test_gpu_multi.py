@@ -18,7 +18,7 @@ def test_slabs_match_serial_oracle(world):
     # cases whose x extent leaves >= 4 planes per rank and whose BC extrapolation stays inside a slab
     names = "chan3d,cyl3d,chan2d,cyl2d,slipchan3d,sliptunnel2d,sliptunnel3d,fevel2d,fevel3d,fevel2d_tav,tunnel2d_tav"
     if world <= 4:
-        names += ",cav3d_32,cav3d_tav,felid3d"
+        names += ",cav3d_32,cav3d_tav,felid3d,kbc2d_cyl,kbc3d_chan"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29610 + world), os.path.join(HERE, "mgpu_worker.py"), names]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
