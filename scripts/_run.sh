@@ -1,15 +1,9 @@
+# round-end style check on one B200:  gpurun --timeout 900 -- 'bash scripts/_run.sh'
 set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name --format=csv,noheader | head -8
-timeout 700 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "slabs_match" 2>&1 | tail -25 > gpurun_out/s5_tests_multi.log
-cat gpurun_out/s5_tests_multi.log
-for halo in p2p nccl; do
-  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 4 --steps 300 --warmup 20 --halo $halo --no-e2e --no-cpu > gpurun_out/s5_c2_n4_${halo}.json 2> gpurun_out/s5_c2_n4_${halo}.err
-done
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 4 --steps 40 --warmup 5 --workload k27 --no-e2e --no-cpu > gpurun_out/s5_k27_n4.json 2> gpurun_out/s5_k27_n4.err
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 4 --steps 2000 --warmup 20 --res 64 --no-e2e --no-cpu > gpurun_out/s5_c2_64_n4_p2p.json 2> gpurun_out/s5_c2_64_n4_p2p.err
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 4 --steps 2000 --warmup 20 --res 64 --halo nccl --no-e2e --no-cpu > gpurun_out/s5_c2_64_n4_nccl.json 2> gpurun_out/s5_c2_64_n4_nccl.err
-for f in gpurun_out/s5_*.json; do echo $f; python -c "
-import json,sys
-d=json.load(open('$f')); print(round(d['value']), d['ms_per_step'], d['gpu_launches'], d['config']['parallelism'][:60])"; done
-tail -3 gpurun_out/s5_c2_n4_p2p.err
+timeout 800 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s6_tests_gpu.log
+cat gpurun_out/s6_tests_gpu.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s6_smoke.log 2>&1; tail -5 gpurun_out/s6_smoke.log
+timeout 300 python bench.py > gpurun_out/s6_bench_n1.json 2> gpurun_out/s6_bench_n1.err
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/s6_bench_ref.json 2> gpurun_out/s6_bench_ref.err
+cut -c1-300 gpurun_out/s6_bench_n1.json gpurun_out/s6_bench_ref.json
