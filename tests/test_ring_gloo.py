@@ -47,7 +47,9 @@ def _worker(rank, world, port_no, name, q):
         plan = ring.halo_plan(defs, rank, world)
         ring.execute_plan_on_host(dist, plan, lat)
 
-        cx = [(1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 0, 0, 1, -1, -1, 1, 0), (1, -1, 0, 0, 1, -1, 1, -1, 0)][Q == 9]
+        cx = {19: (1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 0, 0, 1, -1, -1, 1, 0), 9: (1, -1, 0, 0, 1, -1, 1, -1, 0),
+              # D3Q27 (src/stdafx.cpp:41-70)
+              27: (1, -1, 0, 0, 0, 0, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, -1, 1, -1, 1, 1, -1, 0)}[Q]
         lo, hi = (x0 - 1) % N, (x0 + cnt) % N
         for v in range(Q):
             if cx[v] == 1:      # pulled from x-1: must be in the low ghost plane
@@ -60,7 +62,7 @@ def _worker(rank, world, port_no, name, q):
                 assert np.isnan(lat[v, 0].numpy()).all() and np.isnan(lat[v, cnt + 1].numpy()).all()
         # bytes on the wire: 5 (3) populations per face instead of the reference's 19 (9)
         sends = [m for m in plan if m["is_send"]]
-        assert len(sends) == (10 if Q == 19 else 6)
+        assert len(sends) == {19: 10, 9: 6, 27: 18}[Q]
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
@@ -69,7 +71,7 @@ def _worker(rank, world, port_no, name, q):
         q.put((rank, "FAIL: " + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("name,world", [("chan3d", 2), ("chan2d", 2), ("cav3d_32", 3)])
+@pytest.mark.parametrize("name,world", [("chan3d", 2), ("chan2d", 2), ("cav3d_32", 3), ("kbc3d_chan", 2)])
 def test_halo_plan_over_gloo(name, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
