@@ -554,13 +554,16 @@ __global__ void __launch_bounds__(64) k_velsrc(const VelSrcArgs a)
 	}
 }
 
+#ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches)
 {
 	if (a.n <= 0) return;
 	k_velsrc<L><<<(a.n + 63) / 64, 64, 0, s>>>(a);
 	if (launches) ++*launches;
 }
+#endif
 
+#ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 // kernel variant = collision operator x Guo forcing x time averages; the reference ties KBC to D2Q9 / D3Q27 and
 // D3Q27 to KBC (inc/definitions.h:299-310), so only those combinations are instantiated
 #define LUMA_DISPATCH_FT(KERNEL, COLL, GRID, THREADS) \
@@ -597,6 +600,7 @@ template <class L> void launch_bc(const StepArgs &a, int coll, bool force, cudaS
 	LUMA_DISPATCH(k_bc, grid, threads);
 	if (launches) ++*launches;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // geometry: cell words from the eType array (+ host- or device-made wall descriptors)
@@ -636,12 +640,14 @@ __global__ void k_cell_words(const GeomArgs g)
 	g.cw[id] = w;
 }
 
+#ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s)
 {
 	const unsigned MK = (unsigned)g.M * (unsigned)g.K;
 	dim3 grid((MK + 255) / 256, (unsigned)(g.p_end - g.p_begin));
 	if (g.p_end > g.p_begin) k_cell_words<L><<<grid, 256, 0, s>>>(g);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // device-side LBM_initGrid for index-described cases (src/GridObj_init_grids.cpp:155-384):
@@ -720,12 +726,14 @@ __global__ void k_synthetic(const SynthArgs a)
 	a.bcdesc[id] = (ec > 0) ? cw_pack_bc(ec, nd, n0, n1, n2) : 0u;
 }
 
+#ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s)
 {
 	const unsigned MK = (unsigned)a.M * (unsigned)a.K;
 	dim3 grid((MK + 127) / 128, (unsigned)a.P);
 	k_synthetic<L><<<grid, 128, 0, s>>>(a);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // layout conversion between LUMA's AoS (inc/IVector.h:94-134) and the device SoA
@@ -760,6 +768,7 @@ __global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict_
 	for (int e = threadIdx.x; e < cnt * Q; e += blockDim.x) aos[c0 * Q + e] = tile[e];
 }
 
+#ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first, long long n, cudaStream_t s)
 {
 	if (n > 0) k_aos_to_soa<L::Q><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(aos, soa, stride, first, n);
@@ -768,6 +777,7 @@ template <class L> void launch_soa_to_aos(const double *soa, double *aos, long l
 {
 	if (n > 0) k_soa_to_aos<L::Q><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(soa, aos, stride, first, n);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // momentum exchange on eSolid sites, ObjectManager::computeLiftDrag(i,j,k,g)
@@ -827,6 +837,7 @@ __global__ void __launch_bounds__(256) k_momex(const double *__restrict__ f, con
 	}
 }
 
+#ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 template <class L> int launch_momex(const double *f_prev, const uint8_t *types, long long stride, int P, int M, int K,
 	int p_begin, int p_end, int x_first, int N, double *partials, int max_blocks, cudaStream_t s)
 {
@@ -837,6 +848,7 @@ template <class L> int launch_momex(const double *f_prev, const uint8_t *types, 
 	k_momex<L><<<blocks, 256, 0, s>>>(f_prev, types, stride, P, M, K, p_begin, p_end, x_first, N, partials);
 	return blocks;
 }
+#endif
 
 // explicit instantiations
 #define LUMA_INST(L) \

@@ -1,0 +1,169 @@
+// TEST INFRASTRUCTURE ONLY -- compiles the product's kernel bodies (luma_b200/csrc/kernels_impl.cuh: k_cell_words,
+// k_step, k_bc, k_velsrc with everything they call) for the HOST and runs them thread by thread in plain loops, so
+// that tests/test_kernels_host_emulation.py can replay every parity case against the oracle without a GPU.  It is a
+// logic check of the device code (index arithmetic, branch ladders, operation order), not an implementation anyone can
+// use: one "thread" at a time, single slab, no streams, no exchange, no C ABI.  Nothing in the product links or loads
+// this file, and the product has no CPU path.  Built with g++ -O2 -ffp-contract=off (no contraction, like -fmad=false).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>      // host-side declarations only (dim3, cudaStream_t)
+
+// what nvcc provides inside kernels
+struct EmuIdx { unsigned x, y, z; };
+static thread_local EmuIdx blockIdx, threadIdx, blockDim, gridDim;
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline void __syncthreads() {}
+#undef __noinline__
+#define __noinline__
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+
+#include "../../luma_b200/csrc/kernels_impl.cuh"
+
+using namespace luma;
+
+// same expressions as make_constants() in luma_b200/csrc/api.cu
+static void make_constants(LbmConst &C, int Q)
+{
+	const volatile double three = 3.0, one = 1.0;
+	const double cs = one / std::sqrt(three);
+	C.cs2 = cs * cs;
+	C.inv_cs2 = 1.0 / C.cs2;
+	C.den = (2.0 * C.cs2) * C.cs2;
+	C.inv_den = 1.0 / C.den;
+	C.k1 = 1.0 - C.cs2;
+	C.k0 = 0.0 - C.cs2;
+	C.w[3] = 0.0;
+	if (Q == 27) { C.w[0] = 2.0 / 27.0; C.w[1] = 1.0 / 54.0; C.w[2] = 1.0 / 216.0; C.w[3] = 8.0 / 27.0; }
+	else if (Q == 19) { C.w[0] = 1.0 / 18.0; C.w[1] = 1.0 / 36.0; C.w[2] = 1.0 / 3.0; }
+	else { C.w[0] = 1.0 / 9.0; C.w[1] = 1.0 / 36.0; C.w[2] = 4.0 / 9.0; }
+	for (int k = 0; k < 4; ++k) C.wden[k] = C.w[k] / C.den;
+}
+
+template <class Fn>
+static void emu_launch(unsigned gx, unsigned gy, unsigned threads, Fn fn)
+{
+	gridDim.x = gx; gridDim.y = gy; gridDim.z = 1;
+	blockDim.x = threads; blockDim.y = 1; blockDim.z = 1;
+	for (unsigned by = 0; by < gy; ++by)
+		for (unsigned bx = 0; bx < gx; ++bx)
+			for (unsigned t = 0; t < threads; ++t)
+			{
+				blockIdx.x = bx; blockIdx.y = by; blockIdx.z = 0;
+				threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
+				fn();
+			}
+}
+
+template <class L, int COLL>
+static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, unsigned gbc)
+{
+	const int key = (force ? 2 : 0) | (a.tav ? 1 : 0);
+	// k_bc first, k_step second: they read fin and write disjoint sites of fout (any order gives the same result)
+	if (a.n_bc > 0)
+	{
+		if (key == 0) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, false, false>(a); });
+		else if (key == 1) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, false, true>(a); });
+		else if (key == 2) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, false>(a); });
+		else emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, true>(a); });
+	}
+	if (key == 0) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, false>(a); });
+	else if (key == 1) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, true>(a); });
+	else if (key == 2) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, true, false>(a); });
+	else emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, true, true>(a); });
+}
+
+extern "C" {
+
+struct EmuCase
+{
+	int32_t Q, D, P, M, K;
+	int32_t regularised, coll, force, gravity_dir, velramp_on, general;
+	double omega, rhoin, rho_out, gravity, csmag;
+	double ramp, ramp_t, t_now, t_next;
+};
+
+int emu_class_shift(int Q) { return Q == 27 ? CW<D3Q27>::CLASS_SHIFT : CW<D3Q19>::CLASS_SHIFT; }
+
+int emu_cell_words(const EmuCase *c, const uint8_t *types, const uint32_t *bcdesc, uint32_t *cw)
+{
+	GeomArgs g;
+	memset(&g, 0, sizeof(g));
+	g.types = types; g.bcdesc = bcdesc; g.cw = cw;
+	g.P = c->P; g.M = c->M; g.K = c->K; g.wrap_x = 1; g.p_begin = 0; g.p_end = c->P; g.regularised = c->regularised;
+	const unsigned MK = (unsigned)c->M * (unsigned)c->K;
+	const unsigned gx = (MK + 255) / 256;
+	if (c->Q == 19) emu_launch(gx, c->P, 256, [&] { k_cell_words<D3Q19>(g); });
+	else if (c->Q == 27) emu_launch(gx, c->P, 256, [&] { k_cell_words<D3Q27>(g); });
+	else emu_launch(gx, c->P, 256, [&] { k_cell_words<D2Q9>(g); });
+	return 0;
+}
+
+// one time step of a single slab (the argument block is filled the way luma_b200_step fills it, api.cu)
+int emu_step(const EmuCase *c, const double *fin, double *fout, const uint32_t *cw, double *rho, double *u, long long stride,
+	const long long *bc_list, const int *bc_extra, int n_bc, const double *uin, const uint8_t *types, const uint32_t *bcdesc, double *tav)
+{
+	StepArgs a;
+	memset(&a, 0, sizeof(a));
+	make_constants(a.C, c->Q);
+	a.fin = fin; a.fout = fout; a.cw = cw; a.rho = rho; a.u = u; a.stride = stride;
+	a.P = c->P; a.M = c->M; a.K = c->K; a.MK = (unsigned)c->M * (unsigned)c->K;
+	a.wrap_x = 1; a.p0 = 0; a.pstep = 1; a.write_macro = 1;
+	for (int v = 0; v < c->Q; ++v)
+	{
+		const int cx = c->Q == 19 ? D3Q19::c(v, 0) : (c->Q == 27 ? D3Q27::c(v, 0) : D2Q9::c(v, 0));
+		const int cy = c->Q == 19 ? D3Q19::c(v, 1) : (c->Q == 27 ? D3Q27::c(v, 1) : D2Q9::c(v, 1));
+		const int cz = c->Q == 19 ? D3Q19::c(v, 2) : (c->Q == 27 ? D3Q27::c(v, 2) : D2Q9::c(v, 2));
+		a.off_pull[v] = 8LL * ((long long)v * stride - ((long long)cx * a.MK + (long long)cy * c->K + cz));
+	}
+	a.bc_list = bc_list; a.bc_extra = bc_extra; a.n_bc = n_bc; a.uin = uin;
+	a.rho_out = c->rho_out;
+	a.types = types; a.bcdesc = bcdesc; a.general = c->general; a.regularised = c->regularised; a.velramp_on = c->velramp_on;
+	a.tav = tav;
+	if (c->force) { a.F[c->gravity_dir] = c->rhoin * c->gravity * 1.0; a.hF[c->gravity_dir] = 0.5 * a.F[c->gravity_dir]; }
+	a.smag_coef = 2.0 * 1.4142135623730950488016887242097 * (c->csmag * c->csmag) * c->rhoin * a.C.cs2 * a.C.cs2;
+	a.omega = c->omega;
+	a.tau = 1.0 / c->omega;
+	for (int k = 0; k < 4; ++k) a.lam[k] = (1 - 0.5 * c->omega) * (a.C.w[k] / a.C.cs2);
+	a.kbc_beta_m1 = 2.0 / c->omega;
+	a.kbc_inv_beta = 1.0 / a.kbc_beta_m1;
+	a.ramp = c->ramp; a.ramp_t = c->ramp_t; a.t_now = c->t_now; a.t_next = c->t_next;
+
+	const unsigned gx = (a.MK + STEP_THREADS - 1) / STEP_THREADS, gy = (unsigned)c->P, gbc = (unsigned)((n_bc + 63) / 64);
+	const bool force = c->force != 0;
+	if (c->Q == 27) step_ft<D3Q27, COLL_KBC>(a, force, gx, gy, gbc);
+	else if (c->Q == 19)
+	{
+		if (c->coll == COLL_KBC) return 1;
+		if (c->coll == COLL_SMAG) step_ft<D3Q19, COLL_SMAG>(a, force, gx, gy, gbc);
+		else step_ft<D3Q19, COLL_BGK>(a, force, gx, gy, gbc);
+	}
+	else
+	{
+		if (c->coll == COLL_KBC) step_ft<D2Q9, COLL_KBC>(a, force, gx, gy, gbc);
+		else if (c->coll == COLL_SMAG) step_ft<D2Q9, COLL_SMAG>(a, force, gx, gy, gbc);
+		else step_ft<D2Q9, COLL_BGK>(a, force, gx, gy, gbc);
+	}
+	return 0;
+}
+
+// stored u of the forced-equilibrium inlet sites after a step (k_velsrc)
+int emu_velsrc(const EmuCase *c, const long long *list, int n, const uint8_t *types, const uint32_t *bcdesc, double *u, long long stride,
+	const double *uin, int N)
+{
+	if (n <= 0) return 0;
+	VelSrcArgs a;
+	memset(&a, 0, sizeof(a));
+	a.list = list; a.n = n; a.types = types; a.bcdesc = bcdesc; a.u = u; a.stride = stride; a.uin = uin; a.ramp_t = c->ramp_t;
+	a.P = c->P; a.M = c->M; a.K = c->K; a.N = N; a.wrap_x = 1; a.x_first = 0;
+	const unsigned g = (unsigned)((n + 63) / 64);
+	if (c->Q == 19) emu_launch(g, 1, 64, [&] { k_velsrc<D3Q19>(a); });
+	else if (c->Q == 27) emu_launch(g, 1, 64, [&] { k_velsrc<D3Q27>(a); });
+	else emu_launch(g, 1, 64, [&] { k_velsrc<D2Q9>(a); });
+	return 0;
+}
+
+int emu_lattice_c(int Q, int v, int d) { return Q == 9 ? D2Q9::c(v, d) : (Q == 19 ? D3Q19::c(v, d) : D3Q27::c(v, d)); }
+
+}  // extern "C"
