@@ -57,17 +57,18 @@ static void emu_launch(unsigned gx, unsigned gy, unsigned threads, Fn fn)
 }
 
 template <class L, int COLL>
-static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, unsigned gbc)
+static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, unsigned gbc, bool run_bc)
 {
 	const int key = (force ? 2 : 0) | (a.tav ? 1 : 0);
 	// k_bc first, k_step second: they read fin and write disjoint sites of fout (any order gives the same result)
-	if (a.n_bc > 0)
+	if (a.n_bc > 0 && run_bc)
 	{
 		if (key == 0) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, false, false>(a); });
 		else if (key == 1) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, false, true>(a); });
 		else if (key == 2) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, false>(a); });
 		else emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, true>(a); });
 	}
+	if (gy == 0) return;
 	if (key == 0) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, false>(a); });
 	else if (key == 1) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, true>(a); });
 	else if (key == 2) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, true, false>(a); });
@@ -78,10 +79,14 @@ extern "C" {
 
 struct EmuCase
 {
-	int32_t Q, D, P, M, K;
+	int32_t Q, D, P, M, K;          // P = local planes (with the two ghost planes when wrap_x == 0)
 	int32_t regularised, coll, force, gravity_dir, velramp_on, general;
 	double omega, rhoin, rho_out, gravity, csmag;
 	double ramp, ramp_t, t_now, t_next;
+	int32_t wrap_x;                 // 1: single slab, periodic wrap inside the array; 0: ghost planes 0 and P-1
+	int32_t p0, pstep, nplanes;     // planes this emu_step call covers with k_step: p0 + n * pstep, n < nplanes
+	int32_t run_bc;                 // run k_bc in this call
+	int32_t N, x_first;             // global x size and global x of local plane 0 (k_velsrc, k_synthetic)
 };
 
 int emu_class_shift(int Q) { return Q == 27 ? CW<D3Q27>::CLASS_SHIFT : CW<D3Q19>::CLASS_SHIFT; }
@@ -91,12 +96,13 @@ int emu_cell_words(const EmuCase *c, const uint8_t *types, const uint32_t *bcdes
 	GeomArgs g;
 	memset(&g, 0, sizeof(g));
 	g.types = types; g.bcdesc = bcdesc; g.cw = cw;
-	g.P = c->P; g.M = c->M; g.K = c->K; g.wrap_x = 1; g.p_begin = 0; g.p_end = c->P; g.regularised = c->regularised;
+	const int ghost = c->wrap_x ? 0 : 1;
+	g.P = c->P; g.M = c->M; g.K = c->K; g.wrap_x = c->wrap_x; g.p_begin = ghost; g.p_end = c->P - ghost; g.regularised = c->regularised;
 	const unsigned MK = (unsigned)c->M * (unsigned)c->K;
-	const unsigned gx = (MK + 255) / 256;
-	if (c->Q == 19) emu_launch(gx, c->P, 256, [&] { k_cell_words<D3Q19>(g); });
-	else if (c->Q == 27) emu_launch(gx, c->P, 256, [&] { k_cell_words<D3Q27>(g); });
-	else emu_launch(gx, c->P, 256, [&] { k_cell_words<D2Q9>(g); });
+	const unsigned gx = (MK + 255) / 256, gy = (unsigned)(g.p_end - g.p_begin);
+	if (c->Q == 19) emu_launch(gx, gy, 256, [&] { k_cell_words<D3Q19>(g); });
+	else if (c->Q == 27) emu_launch(gx, gy, 256, [&] { k_cell_words<D3Q27>(g); });
+	else emu_launch(gx, gy, 256, [&] { k_cell_words<D2Q9>(g); });
 	return 0;
 }
 
@@ -109,7 +115,7 @@ int emu_step(const EmuCase *c, const double *fin, double *fout, const uint32_t *
 	make_constants(a.C, c->Q);
 	a.fin = fin; a.fout = fout; a.cw = cw; a.rho = rho; a.u = u; a.stride = stride;
 	a.P = c->P; a.M = c->M; a.K = c->K; a.MK = (unsigned)c->M * (unsigned)c->K;
-	a.wrap_x = 1; a.p0 = 0; a.pstep = 1; a.write_macro = 1;
+	a.wrap_x = c->wrap_x; a.p0 = c->p0; a.pstep = c->pstep; a.write_macro = 1;
 	for (int v = 0; v < c->Q; ++v)
 	{
 		const int cx = c->Q == 19 ? D3Q19::c(v, 0) : (c->Q == 27 ? D3Q27::c(v, 0) : D2Q9::c(v, 0));
@@ -130,37 +136,56 @@ int emu_step(const EmuCase *c, const double *fin, double *fout, const uint32_t *
 	a.kbc_inv_beta = 1.0 / a.kbc_beta_m1;
 	a.ramp = c->ramp; a.ramp_t = c->ramp_t; a.t_now = c->t_now; a.t_next = c->t_next;
 
-	const unsigned gx = (a.MK + STEP_THREADS - 1) / STEP_THREADS, gy = (unsigned)c->P, gbc = (unsigned)((n_bc + 63) / 64);
-	const bool force = c->force != 0;
-	if (c->Q == 27) step_ft<D3Q27, COLL_KBC>(a, force, gx, gy, gbc);
+	const unsigned gx = (a.MK + STEP_THREADS - 1) / STEP_THREADS, gy = (unsigned)(c->nplanes > 0 ? c->nplanes : 0), gbc = (unsigned)((n_bc + 63) / 64);
+	const bool force = c->force != 0, bc = c->run_bc != 0;
+	if (c->Q == 27) step_ft<D3Q27, COLL_KBC>(a, force, gx, gy, gbc, bc);
 	else if (c->Q == 19)
 	{
 		if (c->coll == COLL_KBC) return 1;
-		if (c->coll == COLL_SMAG) step_ft<D3Q19, COLL_SMAG>(a, force, gx, gy, gbc);
-		else step_ft<D3Q19, COLL_BGK>(a, force, gx, gy, gbc);
+		if (c->coll == COLL_SMAG) step_ft<D3Q19, COLL_SMAG>(a, force, gx, gy, gbc, bc);
+		else step_ft<D3Q19, COLL_BGK>(a, force, gx, gy, gbc, bc);
 	}
 	else
 	{
-		if (c->coll == COLL_KBC) step_ft<D2Q9, COLL_KBC>(a, force, gx, gy, gbc);
-		else if (c->coll == COLL_SMAG) step_ft<D2Q9, COLL_SMAG>(a, force, gx, gy, gbc);
-		else step_ft<D2Q9, COLL_BGK>(a, force, gx, gy, gbc);
+		if (c->coll == COLL_KBC) step_ft<D2Q9, COLL_KBC>(a, force, gx, gy, gbc, bc);
+		else if (c->coll == COLL_SMAG) step_ft<D2Q9, COLL_SMAG>(a, force, gx, gy, gbc, bc);
+		else step_ft<D2Q9, COLL_BGK>(a, force, gx, gy, gbc, bc);
 	}
 	return 0;
 }
 
 // stored u of the forced-equilibrium inlet sites after a step (k_velsrc)
 int emu_velsrc(const EmuCase *c, const long long *list, int n, const uint8_t *types, const uint32_t *bcdesc, double *u, long long stride,
-	const double *uin, int N)
+	const double *uin)
 {
 	if (n <= 0) return 0;
 	VelSrcArgs a;
 	memset(&a, 0, sizeof(a));
 	a.list = list; a.n = n; a.types = types; a.bcdesc = bcdesc; a.u = u; a.stride = stride; a.uin = uin; a.ramp_t = c->ramp_t;
-	a.P = c->P; a.M = c->M; a.K = c->K; a.N = N; a.wrap_x = 1; a.x_first = 0;
+	a.P = c->P; a.M = c->M; a.K = c->K; a.N = c->N; a.wrap_x = c->wrap_x; a.x_first = c->x_first;
 	const unsigned g = (unsigned)((n + 63) / 64);
 	if (c->Q == 19) emu_launch(g, 1, 64, [&] { k_velsrc<D3Q19>(a); });
 	else if (c->Q == 27) emu_launch(g, 1, 64, [&] { k_velsrc<D3Q27>(a); });
 	else emu_launch(g, 1, 64, [&] { k_velsrc<D2Q9>(a); });
+	return 0;
+}
+
+// device-side LBM_initGrid (k_synthetic) of one slab
+int emu_synthetic(const EmuCase *c, const int32_t *wall_type, const int32_t *wall_cells, const double *uin, double ramp0, int no_flow,
+	int has_box, const int32_t *box, uint8_t *types, uint32_t *bcdesc, double *f0, double *f1, double *rho, double *u, long long stride)
+{
+	SynthArgs a;
+	memset(&a, 0, sizeof(a));
+	a.types = types; a.bcdesc = bcdesc; a.f0 = f0; a.f1 = f1; a.rho = rho; a.u = u; a.stride = stride;
+	a.P = c->P; a.M = c->M; a.K = c->K; a.N = c->N; a.x_first = c->x_first;
+	for (int i = 0; i < 6; ++i) { a.wall_type[i] = wall_type[i]; a.wall_cells[i] = wall_cells[i]; a.box[i] = box ? box[i] : 0; }
+	a.uin = uin; a.ramp0 = ramp0; a.rhoin = c->rhoin; a.no_flow = no_flow; a.has_box = has_box;
+	make_constants(a.C, c->Q);
+	const unsigned MK = (unsigned)c->M * (unsigned)c->K;
+	const unsigned gx = (MK + 127) / 128;
+	if (c->Q == 19) emu_launch(gx, c->P, 128, [&] { k_synthetic<D3Q19>(a); });
+	else if (c->Q == 27) emu_launch(gx, c->P, 128, [&] { k_synthetic<D3Q27>(a); });
+	else emu_launch(gx, c->P, 128, [&] { k_synthetic<D2Q9>(a); });
 	return 0;
 }
 
