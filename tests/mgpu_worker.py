@@ -66,7 +66,8 @@ def main():
         defs = defs_from_case(case)
         ref = port.PortGrid(case)
         Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
-        for mode in ("device_init", "upload", "device_init+nccl"):
+        # both state paths and both transports, one handle (= one NCCL communicator bootstrap) each
+        for mode in ("device_init", "upload+nccl"):
             uid = ring.broadcast_unique_id(dist, rank)      # one ncclUniqueId per communicator / handle
             g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
             if not mode.endswith("+nccl"):
@@ -106,7 +107,7 @@ def main():
             g.close(); ref.close()
         dist.barrier()
         if rank == 0:
-            print("mgpu ok: %s on %d GPUs (device_init + upload with peer stores, device_init with NCCL), bit-identical to the serial oracle" % (name, world), flush=True)
+            print("mgpu ok: %s on %d GPUs (device_init with peer stores, upload with NCCL), bit-identical to the serial oracle" % (name, world), flush=True)
     dist.destroy_process_group()
 
 
