@@ -71,6 +71,11 @@ def slab_of(N, world, rank):
     return per * rank, (last if rank == world - 1 else per)
 
 
+class Rejected(Exception):
+    """a case luma_b200_upload / init_synthetic refuses (api.cu finalize_geometry): what the reference L_ERRORs on, or
+    what is loop-order dependent in the reference"""
+
+
 class Slab:
     def __init__(self, case, ref, rank=0, world=1):
         self.L = load()
@@ -171,12 +176,16 @@ class Slab:
                     dt = int(types[di, dj, dk])
                     if never(dt):
                         continue
+                    if t == 9 and i - 2 < pb:
+                        raise Rejected("eExtrapolateRight site within two planes of the low x end of the slab")
                     if dt == 1:
                         forced.add(sid(di, dj, dk))
             if not owned:
                 continue
             if t == 8:
                 general = True
+                if (int(desc[i, j, k]) >> 30) == 0:
+                    raise Rejected("slip site outside every wall region")
                 lst.append(me)
                 continue
             if t == 9:
@@ -191,17 +200,30 @@ class Slab:
                 continue
             d = int(desc[i, j, k])
             ec = d >> 30
-            assert ec >= 1
+            if ec == 0:
+                raise Rejected("regularised BC site not within a wall")
+            if ec > 1 and t == 7:
+                raise Rejected("pressure BC on an edge or corner")
             if ec > 1 or t == 7:
                 n = [((d >> (24 + 2 * a)) & 3) - 1 for a in range(3)]
                 ncalls = (D - 1) if t == 7 else 1
                 for m in (1, 2):
-                    pp = i + m * n[0]
-                    assert pb <= pp < pe, "slab too thin for this case"
-                    idn = sid(pp, j + m * n[1], k + m * n[2])
-                    if idn > me and case.time_averaged:
-                        extra[idn] = extra.get(idn, 0) + ncalls
-                        forced.add(idn)
+                    pp, jj, kk = i + m * n[0], j + m * n[1], k + m * n[2]
+                    gi = self.x0 + (i - self.ghost) + m * n[0]
+                    if gi < 0 or gi >= self.N or jj < 0 or jj >= M or kk < 0 or kk >= K:
+                        raise Rejected("extrapolation site off grid")
+                    if pp < pb or pp >= pe:
+                        raise Rejected("slab too thin: a boundary site extrapolates from a plane owned by another rank")
+                    idn = sid(pp, jj, kk)
+                    tn = int(types[pp, jj, kk])
+                    if tn not in (0, 1):
+                        raise Rejected("a boundary site extrapolates from another boundary site")
+                    if idn > me:
+                        if tn == 0:
+                            raise Rejected("a boundary site extrapolates from an eSolid site with a larger index")
+                        if case.time_averaged:
+                            extra[idn] = extra.get(idn, 0) + ncalls
+                            forced.add(idn)
             lst.append(me)
         full = sorted(lst + sorted(forced))
         self.bc_extra = None
