@@ -29,6 +29,12 @@ PATTERNS_2D = [
     ((V, P, S, S, F, F), (1, 1, 1, 1, 0, 0), False),
     ((F, F, F, F, F, F), (0, 0, 0, 0, 0, 0), True),
     ((F, F, S, S, F, F), (0, 0, 2, 1, 0, 0), True),
+    ((P, V, S, S, F, F), (1, 1, 1, 1, 0, 0), True),
+    ((S, S, V, S, S, S), (1, 1, 1, 1, 1, 1), True),
+    ((V, S, S, S, S, S), (1, 1, 1, 1, 1, 1), True),
+    ((S, V, S, S, S, S), (1, 1, 1, 1, 1, 1), False),
+    ((V, P, S, SL, F, F), (1, 1, 3, 1, 0, 0), True),
+    ((S, S, S, S, S, S), (2, 1, 1, 2, 1, 1), True),
 ]
 PATTERNS_3D = [
     ((S, S, S, V, S, S), (1, 1, 1, 1, 1, 1), True),
@@ -43,6 +49,13 @@ PATTERNS_3D = [
     ((S, S, S, V, S, S), (1, 1, 1, 1, 1, 1), False),
     ((V, P, S, S, S, S), (1, 1, 1, 1, 1, 1), False),
     ((F, F, S, S, F, F), (0, 0, 2, 2, 0, 0), True),
+    ((P, V, S, S, F, F), (1, 1, 1, 1, 0, 0), True),
+    ((S, S, S, S, V, S), (1, 1, 1, 1, 1, 1), True),
+    ((S, S, S, S, S, V), (1, 1, 1, 1, 1, 1), False),
+    ((V, S, S, S, S, S), (1, 1, 1, 1, 1, 1), True),
+    ((F, F, S, S, SL, SL), (0, 0, 1, 2, 1, 1), True),
+    ((V, P, S, S, SL, S), (1, 1, 2, 1, 1, 3), True),
+    ((F, F, F, F, F, F), (0, 0, 0, 0, 0, 0), True),
 ]
 
 
@@ -65,9 +78,14 @@ def random_case(seed):
     has_inlet = V in walls
     box = None
     if rnd.random() < 0.6:
-        i0 = rnd.randint(4, nx - 7)
-        j0 = rnd.randint(2, ny - 4)
-        k0 = rnd.randint(0, max(nz - 3, 0)) if dims == 3 else 0
+        if rnd.random() < 0.7:
+            i0 = rnd.randint(4, nx - 7)
+            j0 = rnd.randint(2, ny - 4)
+            k0 = rnd.randint(0, max(nz - 3, 0)) if dims == 3 else 0
+        else:                                          # anywhere: touching walls, the periodic faces, partly off the grid
+            i0 = rnd.randint(-1, nx - 1)
+            j0 = rnd.randint(-1, ny - 1)
+            k0 = rnd.randint(-1, nz - 1) if dims == 3 else 0
         box = (i0, i0 + rnd.randint(1, 3), j0, j0 + rnd.randint(1, 2), k0, (k0 + rnd.randint(1, 3)) if dims == 3 else 1)
     return Case("fuzz%d" % seed, dims, res, (nx + 0.5) / res, (ny + 0.5) / res, (nz + 0.5) / res if dims == 3 else 1.0,
                 timestep="0.05/%d.0" % res, walls=walls, thick=thick,
