@@ -151,3 +151,25 @@ def test_random_case_one_slab_and_slabs(seed):
                 s.velsrc()
                 _cmp("%s rank %d/%d t%d" % (case.name, s.rank, world, t + 1), s.owned(), ref, slice(s.x0 * MK, (s.x0 + s.cnt) * MK))
     ref.close()
+
+
+@pytest.mark.parametrize("seed", range(0, 120, 3))
+def test_random_case_host_mirror_scalars(seed):
+    """luma_b200.Definitions (the host-side image of definitions.h the ABI is fed from) derives what the reference derives"""
+    case = random_case(seed)
+    d = defs_from_case(case)
+    try:
+        g = port.PortGrid(case)
+    except RuntimeError:
+        pytest.skip("the reference rejects this case (omega >= 2)")
+    assert (d.L_N, d.L_M, d.L_K, d.L_NUM_VELS) == (case.N, case.M, case.K, case.Q)
+    assert d.omega == g.omega and d.nu == g.nu and d.gravity == g.gravity and d.rho_out == g.rho_out
+    for a, b in zip(d.inlet_profiles(), (g.uin(0), g.uin(1), g.uin(2))):
+        assert np.array_equal(a, b)
+    lt = g.lattyp
+    wall = g.wall.reshape(-1, 5)
+    desc = d.boundary_site_descriptors(lt)
+    assert len(desc) == int(np.isin(lt, (6, 7, 8)).sum())
+    for site, ec, nd, n in desc:
+        assert (ec, nd, *n) == tuple(int(v) for v in wall[site]), (case.name, site)
+    g.close()
