@@ -82,11 +82,11 @@ def random_case(seed):
             i0 = rnd.randint(4, nx - 7)
             j0 = rnd.randint(2, ny - 4)
             k0 = rnd.randint(0, max(nz - 3, 0)) if dims == 3 else 0
-        else:                                          # anywhere: touching walls, the periodic faces, partly off the grid
-            i0 = rnd.randint(-1, nx - 1)
-            j0 = rnd.randint(-1, ny - 1)
-            k0 = rnd.randint(-1, nz - 1) if dims == 3 else 0
-        box = (i0, i0 + rnd.randint(1, 3), j0, j0 + rnd.randint(1, 2), k0, (k0 + rnd.randint(1, 3)) if dims == 3 else 1)
+        else:                                          # anywhere on the grid: touching walls and the periodic faces
+            i0 = rnd.randint(0, nx - 1)
+            j0 = rnd.randint(0, ny - 1)
+            k0 = rnd.randint(0, nz - 1) if dims == 3 else 0
+        box = (i0, min(i0 + rnd.randint(1, 3), nx), j0, min(j0 + rnd.randint(1, 2), ny), k0, min(k0 + rnd.randint(1, 3), nz) if dims == 3 else 1)
     return Case("fuzz%d" % seed, dims, res, (nx + 0.5) / res, (ny + 0.5) / res, (nz + 0.5) / res if dims == 3 else 1.0,
                 timestep="0.05/%d.0" % res, walls=walls, thick=thick,
                 ux0=rnd.choice((1.0, 0.7, -1.0)) if walls[0] != V else 1.0, uy0=rnd.choice((0.0, 0.0, 0.3)) if not has_inlet else 0.0,
