@@ -276,8 +276,10 @@ def main_ours(args):
     if world > 1:
         nface = {9: 3, 19: 5, 27: 9}[Q]
         halo = "NCCL send/recv of the %d outgoing populations per face" % nface
-        if args.halo == "p2p":
+        if args.halo in ("p2p", "fused"):
             from luma_b200 import ring
+            if args.halo == "fused":
+                os.environ["LUMA_B200_FUSED_HALO"] = "1"       # read by luma_b200_p2p_attach
             # peer stores need CUDA IPC peer mappings between ring neighbours; where a box cannot provide them every rank
             # falls back to the NCCL exchange together (same kernels, same results: tests/test_gpu_multi.py)
             ok = 1
@@ -300,6 +302,9 @@ def main_ours(args):
             if int(flag.item()) == 1:
                 halo = ("device-initiated: the %d outgoing populations per face stored into the neighbour's ghost plane over "
                         "NVLink (CUDA IPC), arrival flags" % nface)
+                if args.halo == "fused":
+                    halo += "; stores fused into the face kernels' epilogue"
+
             else:
                 # a handle cannot be detached: start over without peer mappings
                 g.close()
@@ -422,7 +427,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5", "k27"], default="c2")
-    ap.add_argument("--halo", choices=["p2p", "nccl"], default="p2p", help="multi-GPU halo exchange: peer stores (default) or NCCL send/recv")
+    ap.add_argument("--halo", choices=["p2p", "nccl", "fused"], default="p2p",
+                    help="multi-GPU halo exchange: peer stores by a copy kernel (default), NCCL send/recv, or (experimental) peer stores "
+                         "fused into the face kernels' epilogue")
     ap.add_argument("--res", type=int, default=None, help="cavity edge per GPU for c2/c5 (scaling studies; not the named config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

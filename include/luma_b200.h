@@ -162,7 +162,10 @@ int  luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128);
  * neighbours (MPI_Allgather / torch.distributed.all_gather), and from then on luma_b200_step stores the outgoing
  * populations straight into the neighbour GPU's ghost planes over NVLink and signals arrival with a flag -- no
  * communication-library call per step.  Needs peer access between neighbouring GPUs (NVSwitch: always); without
- * attach the NCCL send/recv path below runs.  Results are identical either way. */
+ * attach the NCCL send/recv path below runs.  Results are identical either way.
+ * Experimental: with LUMA_B200_FUSED_HALO=1 in the environment at attach time the stores move into the epilogue of the
+ * face-plane kernels (no copy kernel; one flag-publish launch); logic checked on the CPU against the oracle, not yet
+ * measured on hardware, hence off by default. */
 #define LUMA_B200_P2P_BLOB_BYTES 256
 int  luma_b200_p2p_export(luma_b200_t *h, void *blob_256);
 int  luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob_256, const void *right_blob_256);

@@ -124,6 +124,7 @@ struct luma_b200
 	int *halo_timeout = nullptr;           // set by k_halo_wait when a neighbour never showed up
 	PeerMap peer[2];                       // 0 = left (rank-1), 1 = right (rank+1); peer[1] aliases peer[0] when nranks == 2
 	bool p2p = false;
+	bool fused = false;                    // LUMA_B200_FUSED_HALO=1 at attach time: the face kernels store into the neighbours' ghost planes themselves
 	unsigned long long xchg = 0;           // exchanges published so far
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
@@ -453,6 +454,11 @@ int luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob, const void *righ
 		pm.f[0] = (double *)pm.base[0]; pm.f[1] = (double *)pm.base[1]; pm.flags = (unsigned long long *)pm.base[2];
 	}
 	h->p2p = true;
+	{
+		// experimental (not yet measured on hardware): fold the peer stores into the face kernels' epilogue
+		const char *fv = getenv("LUMA_B200_FUSED_HALO");
+		h->fused = fv && *fv && atoi(fv) != 0;
+	}
 	return LUMA_B200_OK;
 }
 
@@ -497,8 +503,18 @@ static int build_halo_plan(const LumaCaseParams &p, std::vector<LumaHaloMsg> &pl
 
 // the same plan executed by this GPU alone: every send becomes stores into the receiver's ghost plane
 // (lattice index `li` on both sides: the ranks step in lockstep), receives become a wait on the arrival flags
-static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s)
+static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s, bool already_stored)
 {
+	if (already_stored)
+	{
+		// fused exchange: k_step_faces / k_bc of this step wrote the neighbours' ghost planes; only the arrival flags remain
+		const unsigned long long value = ++h->xchg;
+		launch_halo_publish(h->peer[0].flags + 1, h->peer[1].flags + 0, value, s);
+		launch_halo_wait(h->flags, value, h->halo_timeout, s);
+		h->st.kernel_launches += 2;
+		CK(cudaGetLastError());
+		return LUMA_B200_OK;
+	}
 	std::vector<LumaHaloMsg> plan;
 	build_halo_plan(h->p, plan);
 	HaloPushArgs a;
@@ -529,9 +545,9 @@ static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s)
 	return LUMA_B200_OK;
 }
 
-static int exchange_populations(luma_b200_t *h, double *lat, cudaStream_t s)
+static int exchange_populations(luma_b200_t *h, double *lat, cudaStream_t s, bool already_stored = false)
 {
-	if (h->p2p && (lat == h->f[0] || lat == h->f[1])) return exchange_populations_p2p(h, lat == h->f[0] ? 0 : 1, s);
+	if (h->p2p && (lat == h->f[0] || lat == h->f[1])) return exchange_populations_p2p(h, lat == h->f[0] ? 0 : 1, s, already_stored);
 	std::vector<LumaHaloMsg> plan;
 	build_halo_plan(h->p, plan);
 	const size_t cnt = (size_t)h->MK;
@@ -1028,6 +1044,18 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 		// slab faces first, then their populations go out on the comm stream while the interior
 		// planes are computed (no overlap exists in the reference: MpiManager.cpp:631 runs after :159)
 		CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
+		const bool fused = h->p2p && h->fused;
+		if (fused)
+		{
+			// the neighbours' copies of the lattice this step writes (the ranks step in lockstep: same lattice index)
+			const int lo = (x.fout == h->f[0]) ? 0 : 1;
+			for (int side = 0; side < 2; ++side)
+			{
+				x.peer_f[side] = h->peer[side].f[lo];
+				x.peer_stride[side] = h->peer[side].stride;
+				x.peer_P[side] = h->peer[side].P;
+			}
+		}
 		StepArgs e = x;
 		e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
 		const int nedge = (owned > 1) ? 2 : 1;
@@ -1043,10 +1071,11 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
 			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
 		}
-		LAT(h->Q, launch_step<L>(e, coll, force, nedge, h->s_main, &h->st.kernel_launches));
+		if (fused) LAT(h->Q, launch_step_faces<L>(e, coll, force, nedge, h->s_main, &h->st.kernel_launches));
+		else LAT(h->Q, launch_step<L>(e, coll, force, nedge, h->s_main, &h->st.kernel_launches));
 		CK(cudaEventRecord(h->ev_edge, h->s_main));
 		CK(cudaStreamWaitEvent(h->s_comm, h->ev_edge, 0));
-		int rc = exchange_populations(h, h->f[h->cur ^ 1], h->s_comm);
+		int rc = exchange_populations(h, x.fout, h->s_comm, fused);
 		if (rc) return rc;
 		CK(cudaEventRecord(h->ev_comm, h->s_comm));
 		LAT(h->Q, main_kernel<L>(h, in, coll, force, owned - 2));

@@ -43,6 +43,11 @@ struct StepArgs
 	int general;              // the grid has eSlip / eExtrapolateRight / forced-equilibrium sources
 	int regularised;          // L_REGULARISED_BOUNDARIES
 	int velramp_on;           // L_VELOCITY_RAMP defined: forced-equilibrium sources take u = u_in[j]*ramp_t
+	// fused halo exchange (k_step_faces, k_bc): the ring neighbours' copies of `fout`, peer-mapped over NVLink;
+	// [0] = left (rank-1), [1] = right (rank+1); nullptr = off (k_halo_push copies the planes afterwards instead)
+	double *peer_f[2];
+	long long peer_stride[2];
+	int peer_P[2];
 	// time-averaged statistics (L_COMPUTE_TIME_AVERAGED_QUANTITIES, optimised.cpp:895-917)
 	double *tav;              // SoA [1 + D + 3D-3][stride]: rho, u_p, u_p*u_q (p <= q) or nullptr
 	double t_now, t_next;     // (double)t and (double)(t + 1) of this step
@@ -112,9 +117,12 @@ struct SynthArgs
 // coll: 0 BGK, 1 BGK + Smagorinsky, 2 KBC (D2Q9 and D3Q27 only; D3Q27 always)
 template <class L> void launch_step(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_bc(const StepArgs &a, int coll, bool force, cudaStream_t s, int64_t *launches);
+// k_step on the slab's face planes that also stores the outgoing populations into the neighbours' ghost planes (a.peer_f)
+template <class L> void launch_step_faces(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
 void launch_halo_push(const HaloPushArgs &a, cudaStream_t s);
 void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s);
+void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value, cudaStream_t s);
 void launch_force_general(uint32_t *cw, const long long *ids, int n, int class_shift, cudaStream_t s);
 void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);

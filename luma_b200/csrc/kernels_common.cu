@@ -58,6 +58,21 @@ __global__ void __launch_bounds__(256) k_halo_push(const HaloPushArgs a)
 	}
 }
 
+// the flag part alone, for the fused exchange: the face kernels (k_step_faces, k_bc) of this step have already stored
+// the populations into the neighbours' ghost planes and have completed (stream order); the release below is cumulative
+// over those stores
+__global__ void k_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(left_flag), "l"(value) : "memory");
+	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(right_flag), "l"(value) : "memory");
+}
+void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value, cudaStream_t s)
+{
+	k_halo_publish<<<1, 32, 0, s>>>(left_flag, right_flag, value);
+}
+
 void launch_halo_push(const HaloPushArgs &a, cudaStream_t s)
 {
 	if (a.nmsg <= 0) return;

@@ -164,6 +164,30 @@ __device__ __forceinline__ void store_populations(const StepArgs &a, const long 
 	for (int v = 0; v < L::Q; ++v) store_pop(reinterpret_cast<double *>(pb + (long long)v * sb), f[v]);
 }
 
+// Fused halo exchange: a site on one of the slab's two face planes also stores the populations that leave the slab
+// straight into the neighbour GPU's ghost plane (peer memory over NVLink) -- c_x = -1 from the first owned plane into
+// the left neighbour's high ghost plane, c_x = +1 from the last owned plane into the right neighbour's low ghost
+// plane: what MpiManager::mpi_communicate packs, sends and unpacks (src/MpiManager.cpp:631-815) becomes part of the
+// producing kernel's epilogue.  Arrival is signalled afterwards by k_halo_publish.
+template <class L>
+__device__ __forceinline__ void store_outgoing(const StepArgs &a, const int p, const unsigned r, const double (&f)[L::Q])
+{
+	if (p == 1 && a.peer_f[0])
+	{
+		double *dst = a.peer_f[0] + (long long)(a.peer_P[0] - 1) * a.MK + r;
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v)
+			if (L::c(v, 0) == -1) dst[(long long)v * a.peer_stride[0]] = f[v];
+	}
+	if (p == a.P - 2 && a.peer_f[1])
+	{
+		double *dst = a.peer_f[1] + r;
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v)
+			if (L::c(v, 0) == 1) dst[(long long)v * a.peer_stride[1]] = f[v];
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-link stream of a site that is, or pulls from, one of the special types -- the full branch
 // ladder of GridObj::_LBM_stream_opt (optimised.cpp:206-297) evaluated from the eType array:
@@ -275,8 +299,8 @@ __device__ __forceinline__ void tavg_update(const StepArgs &a, const long long i
 // ------------------------------------------------------------------------------------------------
 // the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
 // ------------------------------------------------------------------------------------------------
-template <class L, int COLL, bool FORCE, bool TAVG>
-__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_step(const StepArgs a)
+template <class L, int COLL, bool FORCE, bool TAVG, bool PEER>
+__device__ __forceinline__ void step_site(const StepArgs &a)
 {
 	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
 	if (r >= a.MK) return;
@@ -292,12 +316,27 @@ __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_st
 	equilibrium_all<L>(rho, u, a.C, feq);
 	collide<L, COLL, FORCE>(a, id, u, feq, f);
 	store_populations<L>(a, id, f);
+	if (PEER) store_outgoing<L>(a, p, r, f);
 	if (a.write_macro)
 	{
 		a.rho[id] = rho;
 #pragma unroll
 		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
 	}
+}
+
+template <class L, int COLL, bool FORCE, bool TAVG>
+__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_step(const StepArgs a)
+{
+	step_site<L, COLL, FORCE, TAVG, false>(a);
+}
+
+// the same on the two face planes of a slab, with the outgoing populations also stored into the neighbours' ghost
+// planes (fused halo exchange; two planes per step, so its occupancy is irrelevant)
+template <class L, int COLL, bool FORCE, bool TAVG>
+__global__ void __launch_bounds__(STEP_THREADS) k_step_faces(const StepArgs a)
+{
+	step_site<L, COLL, FORCE, TAVG, true>(a);
 }
 
 // new-time rho,u of an extrapolation neighbour: GridObj::_LBM_updateAndExtrapolate +
@@ -458,6 +497,7 @@ __device__ __noinline__ void general_site(const StepArgs &a, const int p, const 
 	equilibrium_all<L>(rho, u, a.C, feq);
 	collide<L, COLL, FORCE>(a, id, u, feq, f);
 	store_populations<L>(a, id, f);
+	store_outgoing<L>(a, p, (unsigned)j * (unsigned)a.K + (unsigned)k, f);
 	a.rho[id] = rho;
 #pragma unroll
 	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
@@ -501,6 +541,7 @@ __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 #pragma unroll
 	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = uw[d];
 	store_populations<L>(a, id, f);
+	store_outgoing<L>(a, p, r, f);
 	}
 }
 
@@ -589,6 +630,14 @@ template <class L> void launch_step(const StepArgs &a, int coll, bool force, int
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
 	LUMA_DISPATCH(k_step, grid, STEP_THREADS);
+	if (launches) ++*launches;
+}
+
+template <class L> void launch_step_faces(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches)
+{
+	if (nplanes <= 0) return;
+	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
+	LUMA_DISPATCH(k_step_faces, grid, STEP_THREADS);
 	if (launches) ++*launches;
 }
 
@@ -854,6 +903,7 @@ template <class L> int launch_momex(const double *f_prev, const uint8_t *types, 
 #define LUMA_INST(L) \
 	template void launch_step<L>(const StepArgs &, int, bool, int, cudaStream_t, int64_t *); \
 	template void launch_bc<L>(const StepArgs &, int, bool, cudaStream_t, int64_t *); \
+	template void launch_step_faces<L>(const StepArgs &, int, bool, int, cudaStream_t, int64_t *); \
 	template void launch_velsrc<L>(const VelSrcArgs &, cudaStream_t, int64_t *); \
 	template void launch_cell_words<L>(const GeomArgs &, cudaStream_t); \
 	template void launch_synthetic<L>(const SynthArgs &, cudaStream_t); \

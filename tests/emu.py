@@ -27,7 +27,8 @@ class EmuCase(C.Structure):
                 ("omega", C.c_double), ("rhoin", C.c_double), ("rho_out", C.c_double), ("gravity", C.c_double), ("csmag", C.c_double),
                 ("ramp", C.c_double), ("ramp_t", C.c_double), ("t_now", C.c_double), ("t_next", C.c_double),
                 ("wrap_x", C.c_int32), ("p0", C.c_int32), ("pstep", C.c_int32), ("nplanes", C.c_int32), ("run_bc", C.c_int32),
-                ("N", C.c_int32), ("x_first", C.c_int32)]
+                ("N", C.c_int32), ("x_first", C.c_int32),
+                ("faces", C.c_int32), ("peer_P", C.c_int32 * 2), ("peer_stride", C.c_longlong * 2), ("peer_f", C.c_void_p * 2)]
 
 
 _lib = None
@@ -262,9 +263,21 @@ class Slab:
     def step_all(self):
         self._step(self.ghost, 1, self.cnt, True)
 
-    def step_faces(self):
-        """the launches of enqueue_step() before the exchange: k_bc and k_step on the two face planes"""
+    def step_faces(self, left=None, right=None):
+        """the launches of enqueue_step() before the exchange: k_bc and k_step on the two face planes.  With the
+        neighbour slabs given, the fused exchange: k_bc / k_step_faces store the outgoing populations into the neighbours'
+        ghost planes themselves (here plain host arrays stand in for the peer-mapped lattices)"""
+        p = self.p
+        if left is not None:
+            for side, nb in enumerate((left, right)):
+                p.peer_f[side] = nb.f[nb.cur ^ 1].ctypes.data
+                p.peer_stride[side] = nb.stride
+                p.peer_P[side] = nb.P
+            p.faces = 1
         self._step(1, max(self.cnt - 1, 1), 2 if self.cnt > 1 else 1, True)
+        p.faces = 0
+        for side in range(2):
+            p.peer_f[side] = None
 
     def step_interior(self):
         self._step(2, 1, self.cnt - 2, False)

@@ -57,7 +57,7 @@ static void emu_launch(unsigned gx, unsigned gy, unsigned threads, Fn fn)
 }
 
 template <class L, int COLL>
-static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, unsigned gbc, bool run_bc)
+static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, unsigned gbc, bool run_bc, bool faces)
 {
 	const int key = (force ? 2 : 0) | (a.tav ? 1 : 0);
 	// k_bc first, k_step second: they read fin and write disjoint sites of fout (any order gives the same result)
@@ -69,6 +69,14 @@ static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, uns
 		else emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, true>(a); });
 	}
 	if (gy == 0) return;
+	if (faces)
+	{
+		if (key == 0) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, false, false>(a); });
+		else if (key == 1) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, false, true>(a); });
+		else if (key == 2) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, true, false>(a); });
+		else emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, true, true>(a); });
+		return;
+	}
 	if (key == 0) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, false>(a); });
 	else if (key == 1) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, true>(a); });
 	else if (key == 2) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, true, false>(a); });
@@ -87,6 +95,11 @@ struct EmuCase
 	int32_t p0, pstep, nplanes;     // planes this emu_step call covers with k_step: p0 + n * pstep, n < nplanes
 	int32_t run_bc;                 // run k_bc in this call
 	int32_t N, x_first;             // global x size and global x of local plane 0 (k_velsrc, k_synthetic)
+	// fused halo exchange: the two neighbour slabs' output lattices (here: other arrays of the same process)
+	int32_t faces;                  // run k_step_faces instead of k_step
+	int32_t peer_P[2];
+	long long peer_stride[2];
+	double *peer_f[2];
 };
 
 int emu_class_shift(int Q) { return Q == 27 ? CW<D3Q27>::CLASS_SHIFT : CW<D3Q19>::CLASS_SHIFT; }
@@ -135,21 +148,22 @@ int emu_step(const EmuCase *c, const double *fin, double *fout, const uint32_t *
 	a.kbc_beta_m1 = 2.0 / c->omega;
 	a.kbc_inv_beta = 1.0 / a.kbc_beta_m1;
 	a.ramp = c->ramp; a.ramp_t = c->ramp_t; a.t_now = c->t_now; a.t_next = c->t_next;
+	for (int side = 0; side < 2; ++side) { a.peer_f[side] = c->peer_f[side]; a.peer_stride[side] = c->peer_stride[side]; a.peer_P[side] = c->peer_P[side]; }
 
 	const unsigned gx = (a.MK + STEP_THREADS - 1) / STEP_THREADS, gy = (unsigned)(c->nplanes > 0 ? c->nplanes : 0), gbc = (unsigned)((n_bc + 63) / 64);
-	const bool force = c->force != 0, bc = c->run_bc != 0;
-	if (c->Q == 27) step_ft<D3Q27, COLL_KBC>(a, force, gx, gy, gbc, bc);
+	const bool force = c->force != 0, bc = c->run_bc != 0, fc = c->faces != 0;
+	if (c->Q == 27) step_ft<D3Q27, COLL_KBC>(a, force, gx, gy, gbc, bc, fc);
 	else if (c->Q == 19)
 	{
 		if (c->coll == COLL_KBC) return 1;
-		if (c->coll == COLL_SMAG) step_ft<D3Q19, COLL_SMAG>(a, force, gx, gy, gbc, bc);
-		else step_ft<D3Q19, COLL_BGK>(a, force, gx, gy, gbc, bc);
+		if (c->coll == COLL_SMAG) step_ft<D3Q19, COLL_SMAG>(a, force, gx, gy, gbc, bc, fc);
+		else step_ft<D3Q19, COLL_BGK>(a, force, gx, gy, gbc, bc, fc);
 	}
 	else
 	{
-		if (c->coll == COLL_KBC) step_ft<D2Q9, COLL_KBC>(a, force, gx, gy, gbc, bc);
-		else if (c->coll == COLL_SMAG) step_ft<D2Q9, COLL_SMAG>(a, force, gx, gy, gbc, bc);
-		else step_ft<D2Q9, COLL_BGK>(a, force, gx, gy, gbc, bc);
+		if (c->coll == COLL_KBC) step_ft<D2Q9, COLL_KBC>(a, force, gx, gy, gbc, bc, fc);
+		else if (c->coll == COLL_SMAG) step_ft<D2Q9, COLL_SMAG>(a, force, gx, gy, gbc, bc, fc);
+		else step_ft<D2Q9, COLL_BGK>(a, force, gx, gy, gbc, bc, fc);
 	}
 	return 0;
 }

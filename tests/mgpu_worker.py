@@ -67,11 +67,17 @@ def main():
         ref = port.PortGrid(case)
         Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
         # both state paths and both transports, one handle (= one NCCL communicator bootstrap) each
-        for mode in ("device_init", "upload+nccl"):
+        modes = ("device_init", "upload+nccl")
+        if os.environ.get("LUMA_TEST_FUSED"):               # experimental fused exchange (not in the default suite until measured)
+            modes += ("device_init+fused",)
+        for mode in modes:
             uid = ring.broadcast_unique_id(dist, rank)      # one ncclUniqueId per communicator / handle
             g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
             if not mode.endswith("+nccl"):
+                if mode.endswith("+fused"):
+                    os.environ["LUMA_B200_FUSED_HALO"] = "1"    # read by luma_b200_p2p_attach
                 ring.attach_p2p(dist, g, rank, world)       # device-initiated halo exchange; "+nccl" keeps send/recv
+                os.environ.pop("LUMA_B200_FUSED_HALO", None)
             x0, cnt = g.x_offset, g.x_count
             ref = port.PortGrid(case)
             if mode.startswith("device_init"):

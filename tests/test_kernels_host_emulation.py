@@ -114,3 +114,36 @@ def test_slabs_with_ghost_planes_and_the_products_halo_plan(name, world):
                 s.velsrc()
                 _compare(name, "t%d rank %d/%d" % (t + 1, s.rank, world), s.owned(), ref, slice(s.x0 * MK, (s.x0 + s.cnt) * MK))
     ref.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", MULTI)
+def test_fused_halo_stores_equal_the_plan_driven_exchange(name, world):
+    """LUMA_B200_FUSED_HALO: k_step_faces / k_bc store the outgoing populations into the neighbours' ghost planes in their
+    epilogue; no copy afterwards.  Same bits as the oracle, hence as the plan-driven exchange."""
+    case = CASES[name]
+    defs = defs_from_case(case)
+    ref = port.PortGrid(case)
+    plans = [ring.halo_plan(defs, r, world) for r in range(world)]
+    slabs = [emu.Slab(case, ref, r, world) for r in range(world)]
+    for s in slabs:
+        (s.upload_from(ref) if world == 3 else s.init_synthetic(ref)).finalize()
+    emu.exchange(slabs, plans, 0)                   # the exchange that ends upload / init is the plane copy in both modes
+    MK = case.M * case.K
+    steps = 10 if not case.kbc else 8
+    if case.N * MK * steps > SITE_STEP_BUDGET:
+        steps = 4
+    for t in range(steps):
+        ref.step(1)
+        for s in slabs:
+            s.set_scalars(ref, ref.omega)
+        for r, s in enumerate(slabs):
+            s.step_faces(left=slabs[(r - 1) % world], right=slabs[(r + 1) % world])
+        for s in slabs:
+            s.step_interior()
+            s.advance()
+        if t in (0, 1, steps - 1):
+            for s in slabs:
+                s.velsrc()
+                _compare(name, "fused t%d rank %d/%d" % (t + 1, s.rank, world), s.owned(), ref, slice(s.x0 * MK, (s.x0 + s.cnt) * MK))
+    ref.close()
