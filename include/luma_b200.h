@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LUMA_B200_ABI_VERSION 3
+#define LUMA_B200_ABI_VERSION 4
 
 /* ---- status codes (luma_b200_strerror gives the text; the shim maps non-zero to L_ERROR,
  *      inc/stdafx.h:135-149) ---- */
@@ -122,10 +122,11 @@ typedef struct LumaSyntheticCase {
 } LumaSyntheticCase;
 
 typedef struct LumaStats {
-	int64_t steps;              /* steps executed through luma_b200_step since create */
-	double  ms_last_call;       /* device time of the last luma_b200_step call (CUDA events) */
-	double  ms_per_step;        /* ms_last_call / nsteps of that call */
-	double  mlups_last_call;    /* owned cells * nsteps / ms_last_call / 1e3 */
+	int64_t steps;              /* steps accepted by luma_b200_step since create */
+	double  ms_last_call;       /* device time (CUDA events) of the steps submitted between the last two read points
+	                               (download*, forces, stats, sync, flush): with step(n); stats() the n steps of that call */
+	double  ms_per_step;        /* ms_last_call / steps in that window */
+	double  mlups_last_call;    /* owned cells * steps / ms_last_call / 1e3 */
 	int64_t kernel_launches;    /* kernels this library launched since create */
 	int64_t halo_bytes_per_step;/* bytes this rank sends per step */
 	int64_t cells;              /* owned cells */
@@ -141,7 +142,9 @@ typedef struct LumaStats {
 #define LUMA_B200_RHO 2u
 #define LUMA_B200_U   4u
 
-/* ---- life cycle ---- */
+/* ---- life cycle.  luma_b200_create stores a handle in *h even when it FAILS (so that luma_b200_last_error can be
+ *      read): the caller must luma_b200_destroy it in that case too; *h is NULL only for argument errors caught
+ *      before any allocation (LUMA_B200_EINVAL from the parameter checks, LUMA_B200_ENOMEM for the handle itself). ---- */
 void luma_b200_default_params(LumaCaseParams *p);
 int  luma_b200_create(luma_b200_t **h, const LumaCaseParams *p);
 void luma_b200_destroy(luma_b200_t *h);
@@ -189,7 +192,12 @@ int  luma_b200_halo_plan(const LumaCaseParams *p, LumaHaloMsg *msgs, int32_t cap
  *      Arrays cover this rank's owned planes, preceded/followed by `halo` extra x-planes
  *      (0 for the serial build, 1 for LUMA's MPI build whose local arrays carry recv layers,
  *      src/MpiManager.cpp:277-282).  u_aos/rho give the stored macroscopic fields (they matter for
- *      sites the kernel never updates).  ux_in/uy_in/uz_in have M entries (NULL = zeros). ---- */
+ *      sites the kernel never updates).  ux_in/uy_in/uz_in have M entries (NULL = zeros).
+ *      f_aos == NULL declares f = feq(rho, u) at EVERY site -- the state LBM_initGrid leaves at t = 0
+ *      (src/GridObj_init_grids.cpp:310-333) when no site had its u changed afterwards (L_NO_FLOW builds; bodies
+ *      labelled after initialisation zero the u of their sites, src/ObjectManager.cpp:333-338): the device then
+ *      evaluates _LBM_equilibrium_opt itself, bit for bit, and 8*Q bytes per site never cross the PCIe bus.
+ *      Steps accepted by luma_b200_step but not yet submitted are dropped (the state is replaced). ---- */
 int  luma_b200_upload(luma_b200_t *h, int32_t halo,
                       const double *f_aos, const double *rho, const double *u_aos,
                       const int32_t *lattyp,
@@ -199,9 +207,16 @@ int  luma_b200_upload(luma_b200_t *h, int32_t halo,
 /* ---- state built on the device (benchmark shapes; also usable as a fast LBM_initGrid) ---- */
 int  luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c);
 
-/* ---- nsteps calls of LBM_multi_opt (+ the exchange).  rho/u are kept in registers and stored
- *      only by the last step of the call, which is when the host may look (main_lbm.cpp:449-561). ---- */
+/* ---- nsteps calls of LBM_multi_opt (+ the exchange).  NEVER waits for the GPU: the call advances GridObj::t /
+ *      omega / nu on the host (luma_b200_get_time) and queues the steps.  Submission is lazy -- the most recent step
+ *      is held back until the next call or read point, because the last step before the host looks at the fields is
+ *      the one that stores rho,u (all others keep them in registers; the host may look at main_lbm.cpp:449-561), and
+ *      launch-bound grids collect LUMA_B200_GRAPH_STEPS steps into one CUDA-graph launch even when the host calls
+ *      once per step (src/main_lbm.cpp:441).  Every entry point that reads state -- download*, forces, stats, sync --
+ *      submits what is held back first; luma_b200_flush submits without reading or waiting (call it before a long
+ *      stretch of host work).  A halo time-out (dead ring neighbour) is reported by the next call that notices it. ---- */
 int  luma_b200_step(luma_b200_t *h, int32_t nsteps);
+int  luma_b200_flush(luma_b200_t *h);
 
 /* ---- state out, same layout/halo convention as upload; only owned planes are written.
  *      `what` = LUMA_B200_F | LUMA_B200_RHO | LUMA_B200_U; unused pointers may be NULL. ---- */
@@ -228,7 +243,9 @@ int  luma_b200_upload_timeav(luma_b200_t *h, int32_t halo, const double *rho_tim
 int  luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu);
 
 /* ---- momentum-exchange force on bounce-back bodies accumulated by the LAST step
- *      (ObjectManager::computeLiftDrag(i,j,k,g), src/ObjectManager.cpp:93-164), this rank's part ---- */
+ *      (ObjectManager::computeLiftDrag(i,j,k,g), src/ObjectManager.cpp:93-164), this rank's part: the links whose
+ *      FLUID end this rank owns (the sum over ranks is the reference's sum).  Needs no barrier between the ranks:
+ *      only this rank's own planes of the previous lattice are read. ---- */
 int  luma_b200_forces(luma_b200_t *h, double F[3]);
 
 int  luma_b200_stats(luma_b200_t *h, LumaStats *s);

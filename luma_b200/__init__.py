@@ -9,5 +9,12 @@ from .definitions import Definitions, eExtrapolateRight, eFluid, ePressure, eSli
 from .gridobj import GridObj, comm_unique_id  # noqa: F401
 from . import capi  # noqa: F401
 
-__all__ = ["Definitions", "GridObj", "comm_unique_id", "capi", "eSolid", "eFluid", "eVelocity", "ePressure", "eSlip",
+
+def kernel_fingerprint() -> str:
+    """sha256 over the CUDA sources and nvcc flags the loaded library was built from: profiles/ncu_summary.json is
+    stamped with it, so that bench.py quotes an ncu DRAM-traffic figure only for the kernel build it was measured on."""
+    from . import build
+    return build._src_hash()
+
+__all__ = ["Definitions", "GridObj", "comm_unique_id", "capi", "kernel_fingerprint", "eSolid", "eFluid", "eVelocity", "ePressure", "eSlip",
            "eExtrapolateRight"]

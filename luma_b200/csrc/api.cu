@@ -107,21 +107,30 @@ struct luma_b200
 	size_t staging_bytes = 0;
 	double *momex_dev = nullptr;
 	cudaStream_t s_main = nullptr, s_comm = nullptr, s_copy = nullptr;
-	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_snap = nullptr, ev_copied = nullptr, ev_fork = nullptr;
+	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_int = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_snap = nullptr, ev_copied = nullptr,
+		ev_fork = nullptr, ev_join = nullptr;
 	double *snap = nullptr;         // snapshot of rho / u (AoS) / f (AoS) feeding an asynchronous download
 	size_t snap_bytes = 0;
 	bool copy_pending = false;
 	ncclComm_t comm = nullptr;
 	LbmConst C;
-	double omega = 0.0, nu = 0.0;
-	int t = 0;
+	double omega = 0.0, nu = 0.0;       // GridObj::omega, ::nu after the steps accepted so far (host arithmetic)
+	int t = 0;                          // GridObj::t: steps accepted by luma_b200_step (upload's t + ...)
+	int t_enq = 0;                      // time level reached by the work ENQUEUED so far; t - t_enq steps are deferred
+	double omega_enq = 0.0;             // omega of the last enqueued step (Reynolds ramp)
+	bool timing_open = false;           // ev_t0 recorded, ev_t1 not yet: steps have been enqueued since the last read point
+	int timed_steps = 0;                // steps enqueued since ev_t0
+	bool stream_joined = true;          // s_main has waited for everything issued on s_comm
+	bool stats_dirty = false;           // a closed timing window (ev_t0 .. ev_t1) has not been read yet
+	int window_steps = 0;               // steps inside that window
 	bool have_state = false;
 	bool stepped = false;
 	LumaStats st;
 	std::string err;
 	// device-initiated halo exchange (NVLink peer stores); falls back to NCCL send/recv when not attached
 	unsigned long long *flags = nullptr;   // [0] exchange number that arrived from the left neighbour, [1] from the right; +4: counter
-	int *halo_timeout = nullptr;           // set by k_halo_wait when a neighbour never showed up
+	int *halo_timeout = nullptr;           // set by k_halo_wait when a neighbour never showed up (device view of a mapped host word)
+	volatile int *halo_timeout_host = nullptr;   // the same word as the host reads it: polled without any stream traffic
 	PeerMap peer[2];                       // 0 = left (rank-1), 1 = right (rank+1); peer[1] aliases peer[0] when nranks == 2
 	bool p2p = false;
 	bool fused = false;                    // LUMA_B200_FUSED_HALO=1 at attach time: the face kernels store into the neighbours' ghost planes themselves
@@ -189,7 +198,7 @@ static cudaEvent_t prof_event(luma_b200_t *h)
 	else { using L = D2Q9; CALL; } } while (0)
 
 template <class L>
-static void main_kernel(luma_b200_t *h, const StepArgs &a, int coll, bool force, int nplanes)
+static void main_kernel(luma_b200_t *h, const StepArgs &a, int coll, int force, int nplanes)
 {
 	if (h->profiling && nplanes > 0) cudaEventRecord(prof_event(h), h->s_main);
 	launch_step<L>(a, coll, force, nplanes, h->s_main, &h->st.kernel_launches);
@@ -199,6 +208,13 @@ static void main_kernel(luma_b200_t *h, const StepArgs &a, int coll, bool force,
 		h->st.step_kernel_launches++;
 		h->st.step_kernel_cells += (long long)nplanes * h->MK;
 	}
+}
+
+static int halo_health(luma_b200_t *h)
+{
+	if (h->halo_timeout_host && *h->halo_timeout_host)
+		FAIL(LUMA_B200_ENCCL, "halo exchange: a ring neighbour did not deliver its populations within 20 s");
+	return LUMA_B200_OK;
 }
 
 extern "C" {
@@ -269,6 +285,8 @@ static void free_all(luma_b200_t *h)
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
 	if (h->ev_snap) cudaEventDestroy(h->ev_snap);
 	if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+	if (h->ev_join) cudaEventDestroy(h->ev_join);
+	if (h->ev_int) cudaEventDestroy(h->ev_int);
 	if (h->ev_copied) cudaEventDestroy(h->ev_copied);
 	if (h->s_copy) cudaStreamDestroy(h->s_copy);
 	cudaFree(h->snap);
@@ -276,7 +294,8 @@ static void free_all(luma_b200_t *h)
 	for (GraphSlot &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
 	for (int side = 0; side < 2; ++side)
 		for (void *&b : h->peer[side].base) { if (b) cudaIpcCloseMemHandle(b); b = nullptr; }
-	cudaFree(h->flags); cudaFree(h->halo_timeout);
+	cudaFree(h->flags);
+	if (h->halo_timeout_host) cudaFreeHost((void *)h->halo_timeout_host);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_comm) cudaStreamDestroy(h->s_comm);
 }
@@ -342,6 +361,8 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
 	CK(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
 	const size_t fbytes = (size_t)h->stride * h->Q * sizeof(double);
 	cudaError_t e = cudaMalloc(&h->f[0], fbytes);
@@ -354,7 +375,15 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	if (e == cudaSuccess) e = cudaMalloc(&h->uin, (size_t)3 * p->M * sizeof(double));
 	if (e == cudaSuccess) e = cudaMalloc(&h->momex_dev, (size_t)3 * 4096 * sizeof(double));
 	if (e == cudaSuccess && h->ghost) e = cudaMalloc(&h->flags, 64);
-	if (e == cudaSuccess && h->ghost) e = cudaMalloc(&h->halo_timeout, sizeof(int));
+	if (e == cudaSuccess && h->ghost)
+	{
+		// the time-out word lives in mapped host memory: k_halo_wait stores to it with system scope, the host polls it
+		// without touching a stream (luma_b200_step never synchronises)
+		void *hp = nullptr, *dp = nullptr;
+		e = cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped);
+		if (e == cudaSuccess) { *(int *)hp = 0; h->halo_timeout_host = (volatile int *)hp; e = cudaHostGetDevicePointer(&dp, hp, 0); }
+		if (e == cudaSuccess) h->halo_timeout = (int *)dp;
+	}
 	const size_t tav_bytes = (size_t)h->stride * (1 + h->D + 3 * h->D - 3) * sizeof(double);
 	if (e == cudaSuccess && p->time_averaged) e = cudaMalloc(&h->tav, tav_bytes);
 	if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return LUMA_B200_ENOMEM; }
@@ -363,8 +392,15 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	CK(cudaMemsetAsync(h->uin, 0, (size_t)3 * p->M * sizeof(double), h->s_main));
 	if (h->tav) CK(cudaMemsetAsync(h->tav, 0, tav_bytes, h->s_main));      // init_grids.cpp:304-306
 	if (h->flags) CK(cudaMemsetAsync(h->flags, 0, 64, h->s_main));
-	if (h->halo_timeout) CK(cudaMemsetAsync(h->halo_timeout, 0, sizeof(int), h->s_main));
+	// both lattices start as zeros: ghost planes and never-updated sites hold the same, defined bits whichever way the
+	// state arrives (upload or init_synthetic) -- nothing reads them, but nothing should depend on cudaMalloc's leftovers
+	CK(cudaMemsetAsync(h->f[0], 0, fbytes, h->s_main));
+	CK(cudaMemsetAsync(h->f[1], 0, fbytes, h->s_main));
+	CK(cudaMemsetAsync(h->rho, 0, (size_t)h->stride * sizeof(double), h->s_main));
+	CK(cudaMemsetAsync(h->u, 0, (size_t)h->stride * h->D * sizeof(double), h->s_main));
+	CK(cudaMemsetAsync(h->types, 0, (size_t)h->cells, h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
+	h->t_enq = h->t; h->omega_enq = h->omega;
 	return LUMA_B200_OK;
 }
 
@@ -787,10 +823,15 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	const double *ux_in, const double *uy_in, const double *uz_in)
 {
 	if (!h) return LUMA_B200_EINVAL;
-	if (!f_aos || !rho || !u_aos || !lattyp || halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "upload: null array or bad halo");
+	if (!rho || !u_aos || !lattyp || halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "upload: null array or bad halo");
 	if (n_bc && !bc_sites) FAIL(LUMA_B200_EINVAL, "upload: bc_sites");
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
+	// the state is replaced: steps accepted but not yet submitted are dropped, running ones are waited for
+	h->t_enq = h->t; h->timing_open = false; h->stats_dirty = false; h->prof_used = 0;
+	CK(cudaStreamSynchronize(h->s_comm));
+	CK(cudaStreamSynchronize(h->s_main));
+	h->stream_joined = true;
 	const long long owned = (long long)p.x_count * h->MK;
 	const long long host_off = (long long)halo * h->MK;       // first owned site in the host arrays
 	const long long dev_off = (long long)h->ghost * h->MK;    // first owned site on the device
@@ -801,7 +842,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(192u << 20) / (h->Q * 8)));
 	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
 	if (rc) return rc;
-	for (long long c0 = 0; c0 < owned; c0 += chunk)
+	for (long long c0 = 0; f_aos && c0 < owned; c0 += chunk)
 	{
 		const long long n = std::min(chunk, owned - c0);
 		CK(cudaMemcpyAsync(h->staging, f_aos + (host_off + c0) * h->Q, (size_t)n * h->Q * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
@@ -823,7 +864,14 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 		launch_types_from_i32((const int32_t *)h->staging, h->types + dev_off + c0, n, h->s_main);
 		h->st.kernel_launches++;
 	}
-	CK(cudaMemcpyAsync(h->f[1], h->f[0], (size_t)h->stride * h->Q * sizeof(double), cudaMemcpyDeviceToDevice, h->s_main));
+	if (!f_aos)
+	{
+		// f_aos == NULL: the host declares f = feq(rho, u) at every site, which is what LBM_initGrid leaves at t = 0
+		// (src/GridObj_init_grids.cpp:310-333); the device evaluates the same expression bit for bit (k_feq_init uses
+		// the step's own equilibrium_all) and 19 x 8 B per site stay off the PCIe bus
+		LAT(h->Q, launch_feq_init<L>(h->rho, h->u, h->f[0], h->stride, dev_off, owned, h->C, h->s_main));
+		h->st.kernel_launches++;
+	}
 	h->cur = 0;
 
 	// inlet profiles (inc/GridObj.h:76-78)
@@ -885,12 +933,16 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	{
 		rc = exchange_populations(h, h->f[h->cur], h->s_main);
 		if (rc) return rc;
-		CK(cudaStreamSynchronize(h->s_main));
 	}
-	h->t = p.t; h->omega = p.omega;
+	// lattice 1 = lattice 0, ghost planes included (f.swap(fNew) keeps never-updated sites identical in both,
+	// optimised.cpp:159 and init_grids.cpp:333)
+	CK(cudaMemcpyAsync(h->f[1], h->f[0], (size_t)h->stride * h->Q * sizeof(double), cudaMemcpyDeviceToDevice, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	h->t = p.t; h->omega = p.omega; h->t_enq = h->t; h->omega_enq = h->omega;
+	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 	h->have_state = true; h->stepped = false;
 	++h->geometry_epoch;
-	return LUMA_B200_OK;
+	return halo_health(h);
 }
 
 int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
@@ -898,6 +950,10 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 	if (!h || !c) return LUMA_B200_EINVAL;
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
+	h->t_enq = h->t; h->timing_open = false; h->stats_dirty = false; h->prof_used = 0;
+	CK(cudaStreamSynchronize(h->s_comm));
+	CK(cudaStreamSynchronize(h->s_main));
+	h->stream_joined = true;
 	for (int a = 0; a < 6; ++a)
 	{
 		const int t = c->wall_type[a];
@@ -944,32 +1000,24 @@ int luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c)
 		return (ec > 0) ? cw_pack_bc(ec, nd, n0, n1, n2) : 0u;
 	});
 	if (rc) return rc;
-	h->t = p.t; h->omega = p.omega;
+	h->t = p.t; h->omega = p.omega; h->t_enq = h->t; h->omega_enq = h->omega;
+	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 	h->have_state = true; h->stepped = false;
 	++h->geometry_epoch;
 	return LUMA_B200_OK;
 }
 
-int luma_b200_set_profiling(luma_b200_t *h, int32_t on)
+// ------------------------------------------------------------------------------------------------
+// The time step.  luma_b200_step() only ACCEPTS steps: it advances GridObj::t / omega / nu on the host and
+// hands work to the GPU without ever waiting for it.  Work is submitted lazily so that
+//   * the last step before the host looks at the fields is the one that stores rho,u (every other step keeps
+//     them in registers), although the host calls LBM_multi_opt() once per step (src/main_lbm.cpp:441);
+//   * launch-bound grids run as CUDA-graph batches even when the steps arrive one call at a time.
+// Every entry point that reads state (download*, forces, stats, sync, flush) submits what is still deferred.
+// ------------------------------------------------------------------------------------------------
+static void fill_step_args(luma_b200_t *h, StepArgs &a)
 {
-	if (!h) return LUMA_B200_EINVAL;
-	h->profiling = on != 0;
-	h->st.step_kernel_launches = 0; h->st.step_kernel_ms = 0.0; h->st.step_kernel_cells = 0;
-	return LUMA_B200_OK;
-}
-
-int luma_b200_step(luma_b200_t *h, int32_t nsteps)
-{
-	if (!h) return LUMA_B200_EINVAL;
-	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "step before upload/init_synthetic");
-	if (nsteps < 0) FAIL(LUMA_B200_EINVAL, "nsteps < 0");
-	if (nsteps == 0) return LUMA_B200_OK;
 	const LumaCaseParams &p = h->p;
-	CK(cudaSetDevice(p.device));
-	const bool force = p.gravity_on != 0;
-	const int coll = p.kbc ? 2 : (p.bgksmag ? 1 : 0);      // optimised.cpp:147-151: the KBC operator replaces _LBM_collide_opt
-
-	StepArgs a;
 	memset(&a, 0, sizeof(a));
 	a.cw = h->cw; a.rho = h->rho; a.u = h->u; a.stride = h->stride;
 	a.P = h->P; a.M = p.M; a.K = p.K; a.MK = (unsigned)h->MK;
@@ -986,139 +1034,217 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 	a.velramp_on = p.velocity_ramp_on ? 1 : 0;
 	a.tav = h->tav;
 	// force_xyz = rho_init * gravity * refinement_ratio along L_GRAVITY_DIRECTION (init_grids.cpp:296-297)
-	for (int d = 0; d < 3; ++d) { a.F[d] = 0.0; a.hF[d] = 0.0; }
-	if (force) { a.F[p.gravity_dir] = p.rhoin * p.gravity * 1.0; a.hF[p.gravity_dir] = 0.5 * a.F[p.gravity_dir]; }
+	a.Fg = 0.0; a.hFg = 0.0;
+	if (p.gravity_on) { a.Fg = p.rhoin * p.gravity * 1.0; a.hFg = 0.5 * a.Fg; }
 	a.smag_coef = 2.0 * LUMA_SQRT2 * (p.csmag * p.csmag) * p.rhoin * h->C.cs2 * h->C.cs2;
+}
 
-	CK(cudaEventRecord(h->ev_t0, h->s_main));
-	h->prof_used = 0;
-	const int owned = p.x_count;
+// omega / nu of the step that takes the grid from t_now to t_now + 1:
+// _LBM_updateReynolds (optimised.cpp:1313-1321), GridUnits::nud2nulbm (inc/GridUnits.h:128)
+static void reynolds_step(const luma_b200_t *h, int t_now, double &omega, double &nu)
+{
+	const LumaCaseParams &p = h->p;
+	if (!p.reynolds_ramp_on) return;
+	const double newRe = p.re * reynolds_ramp_coef(p, (t_now + 1) * p.dt);
+	nu = ((1.0 / newRe) * p.dt) / (p.dh * p.dh);
+	omega = 1.0 / ((nu / h->C.cs2) + 0.5);
+}
 
-	// per-step scalars of the step that takes the grid from time level t to t+1
-	auto step_scalars = [&](StepArgs &x, int t_now)
+// per-step scalars of the step that takes the grid from time level t_now to t_now + 1
+static void step_scalars(luma_b200_t *h, StepArgs &x, int t_now)
+{
+	const LumaCaseParams &p = h->p;
+	double nu_unused = 0.0;
+	reynolds_step(h, t_now, h->omega_enq, nu_unused);
+	const double om = h->omega_enq;
+	x.omega = om;
+	x.tau = 1.0 / om;
+	for (int k = 0; k < 4; ++k) x.lam[k] = (1 - 0.5 * om) * (h->C.w[k] / h->C.cs2);
+	x.kbc_beta_m1 = 2.0 / om;
+	x.kbc_inv_beta = 1.0 / x.kbc_beta_m1;
+	x.ramp = velocity_ramp_coef(p, (t_now + 1) * p.dt);
+	x.ramp_t = velocity_ramp_coef(p, t_now * p.dt);
+	x.t_now = (double)t_now; x.t_next = (double)(t_now + 1);
+}
+
+static inline int force_code(const LumaCaseParams &p) { return p.gravity_on ? 1 + p.gravity_dir : 0; }
+static inline int coll_code(const LumaCaseParams &p) { return p.kbc ? 2 : (p.bgksmag ? 1 : 0); }   // optimised.cpp:147-151
+
+// One time step on the handle's two streams.
+//   s_comm (highest priority): the list kernel k_bc (velocity / pressure / per-link sites), with slabs also the two
+//           face planes and then the exchange of their outgoing populations;
+//   s_main: k_step over the interior planes (all planes on a single rank).
+// Both read lattice `fin` and write disjoint sites of `fout`, so the two streams run side by side and the exchange
+// hides behind the interior kernel (no overlap exists in the reference: MpiManager.cpp:631 runs after :159).  Each
+// stream waits for what the OTHER stream did in the previous step (ev_edge / ev_int) -- those kernels wrote sites
+// this step reads and read sites this step overwrites.
+static int enqueue_step_live(luma_b200_t *h, StepArgs &x, int coll, int force)
+{
+	const int owned = h->p.x_count;
+	const bool side = h->ghost || h->n_bc > 0;
+	if (side)
 	{
-		if (p.reynolds_ramp_on)
-		{
-			// _LBM_updateReynolds (optimised.cpp:1313-1321), GridUnits::nud2nulbm (inc/GridUnits.h:128)
-			const double newRe = p.re * reynolds_ramp_coef(p, (t_now + 1) * p.dt);
-			h->nu = ((1.0 / newRe) * p.dt) / (p.dh * p.dh);
-			h->omega = 1.0 / ((h->nu / h->C.cs2) + 0.5);
-		}
-		x.omega = h->omega;
-		x.tau = 1.0 / h->omega;
-		for (int k = 0; k < 4; ++k) x.lam[k] = (1 - 0.5 * h->omega) * (h->C.w[k] / h->C.cs2);
-		x.kbc_beta_m1 = 2.0 / h->omega;
-		x.kbc_inv_beta = 1.0 / x.kbc_beta_m1;
-		x.ramp = velocity_ramp_coef(p, (t_now + 1) * p.dt);
-		x.ramp_t = velocity_ramp_coef(p, t_now * p.dt);
-		x.t_now = (double)t_now; x.t_next = (double)(t_now + 1);
-	};
-
-	// one time step enqueued on the handle's streams (also the body of the captured CUDA graph below)
-	auto enqueue_step = [&](StepArgs &x) -> int
-	{
-	// The list kernel (boundary / class-4 sites) and the fluid kernel read the same lattice and write disjoint
-	// sites, so they run side by side: k_bc goes to the high-priority stream, where its latency-bound threads
-	// fill in behind the bandwidth-bound k_step instead of holding the GPU alone at the start of every step.
-	// (with per-kernel profiling events on, k_bc runs first on the main stream so that the events time k_step alone)
-	const bool side = h->n_bc > 0 && !h->profiling;
+		CK(cudaStreamWaitEvent(h->s_main, h->ev_edge, 0));
+		CK(cudaStreamWaitEvent(h->s_comm, h->ev_int, 0));
+		h->stream_joined = false;
+	}
 	if (!h->ghost)
 	{
 		x.p0 = 0; x.pstep = 1;
-		if (!side)
+		if (side && h->profiling)
 		{
+			// per-kernel events on: the list kernel runs first on the main stream so that the events time k_step alone
 			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_main, &h->st.kernel_launches));
 		}
-		if (side)
+		else if (side)
 		{
-			CK(cudaEventRecord(h->ev_fork, h->s_main));
-			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
 			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
-			CK(cudaEventRecord(h->ev_comm, h->s_comm));
+			CK(cudaEventRecord(h->ev_edge, h->s_comm));
 		}
 		LAT(h->Q, main_kernel<L>(h, x, coll, force, h->P));
-		if (side) CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
-	}
-	else
-	{
-		// slab faces first, then their populations go out on the comm stream while the interior
-		// planes are computed (no overlap exists in the reference: MpiManager.cpp:631 runs after :159)
-		CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
-		const bool fused = h->p2p && h->fused;
-		if (fused)
-		{
-			// the neighbours' copies of the lattice this step writes (the ranks step in lockstep: same lattice index)
-			const int lo = (x.fout == h->f[0]) ? 0 : 1;
-			for (int side = 0; side < 2; ++side)
-			{
-				x.peer_f[side] = h->peer[side].f[lo];
-				x.peer_stride[side] = h->peer[side].stride;
-				x.peer_P[side] = h->peer[side].P;
-			}
-		}
-		StepArgs e = x;
-		e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
-		const int nedge = (owned > 1) ? 2 : 1;
-		StepArgs in = x;
-		in.p0 = 2; in.pstep = 1;
-		if (!side)
-		{
-			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_main, &h->st.kernel_launches));
-		}
-		if (side)
-		{
-			CK(cudaEventRecord(h->ev_fork, h->s_main));
-			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
-			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
-		}
-		if (fused) LAT(h->Q, launch_step_faces<L>(e, coll, force, nedge, h->s_main, &h->st.kernel_launches));
-		else LAT(h->Q, launch_step<L>(e, coll, force, nedge, h->s_main, &h->st.kernel_launches));
-		CK(cudaEventRecord(h->ev_edge, h->s_main));
-		CK(cudaStreamWaitEvent(h->s_comm, h->ev_edge, 0));
-		int rc = exchange_populations(h, x.fout, h->s_comm, fused);
-		if (rc) return rc;
-		CK(cudaEventRecord(h->ev_comm, h->s_comm));
-		LAT(h->Q, main_kernel<L>(h, in, coll, force, owned - 2));
-	}
+		if (side) CK(cudaEventRecord(h->ev_int, h->s_main));
 		return LUMA_B200_OK;
-	};
+	}
+	const bool fused = h->p2p && h->fused;
+	if (fused)
+	{
+		// the neighbours' copies of the lattice this step writes (the ranks step in lockstep: same lattice index)
+		const int lo = (x.fout == h->f[0]) ? 0 : 1;
+		for (int sd = 0; sd < 2; ++sd)
+		{
+			x.peer_f[sd] = h->peer[sd].f[lo];
+			x.peer_stride[sd] = h->peer[sd].stride;
+			x.peer_P[sd] = h->peer[sd].P;
+		}
+	}
+	StepArgs e = x;
+	e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
+	const int nedge = (owned > 1) ? 2 : 1;
+	StepArgs in = x;
+	in.p0 = 2; in.pstep = 1;
+	LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
+	if (fused) LAT(h->Q, launch_step_faces<L>(e, coll, force, nedge, h->s_comm, &h->st.kernel_launches));
+	else LAT(h->Q, launch_step<L>(e, coll, force, nedge, h->s_comm, &h->st.kernel_launches));
+	CK(cudaEventRecord(h->ev_edge, h->s_comm));
+	if (h->profiling) CK(cudaStreamWaitEvent(h->s_main, h->ev_edge, 0));      // events on: the interior kernel is timed alone
+	const int rc = exchange_populations(h, x.fout, h->s_comm, fused);
+	if (rc) return rc;
+	CK(cudaEventRecord(h->ev_comm, h->s_comm));
+	LAT(h->Q, main_kernel<L>(h, in, coll, force, owned - 2));
+	CK(cudaEventRecord(h->ev_int, h->s_main));
+	return LUMA_B200_OK;
+}
 
-	// Launch-bound grids (BASELINE configs[0], 256^2: ~3 us of work per step): batches of `graph_steps` steps are
-	// captured once into a CUDA graph -- same kernels, same arguments, the two streams become graph branches -- and
-	// replayed with one launch each.  Only while every per-step scalar is constant (ramps finished, no time
-	// averages, no profiling events), on a single rank, and never for the last step of a call (which stores rho,u).
+// the same step as a self-contained fork/join on the capturing stream (single rank only): the body of the CUDA graphs
+static int enqueue_step_captured(luma_b200_t *h, StepArgs &x, int coll, int force)
+{
+	x.p0 = 0; x.pstep = 1;
+	const bool side = h->n_bc > 0;
+	if (side)
+	{
+		CK(cudaEventRecord(h->ev_fork, h->s_main));
+		CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
+		LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
+		CK(cudaEventRecord(h->ev_join, h->s_comm));
+	}
+	LAT(h->Q, launch_step<L>(x, coll, force, h->P, h->s_main, &h->st.kernel_launches));
+	if (side) CK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+	return LUMA_B200_OK;
+}
+
+// s_main waits for everything issued on s_comm (so that work queued on s_main afterwards sees a complete step)
+static int join_streams(luma_b200_t *h)
+{
+	if (h->stream_joined) return LUMA_B200_OK;
+	CK(cudaStreamWaitEvent(h->s_main, h->ev_edge, 0));
+	if (h->ghost) CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
+	h->stream_joined = true;
+	return LUMA_B200_OK;
+}
+
+// device time of the steps between two read points (ev_t0 .. ev_t1) -> LumaStats, without blocking unless asked to
+static int collect_stats(luma_b200_t *h, bool wait)
+{
+	if (!h->stats_dirty) return LUMA_B200_OK;
+	if (!wait && cudaEventQuery(h->ev_t1) != cudaSuccess) { cudaGetLastError(); return LUMA_B200_OK; }
+	CK(cudaEventSynchronize(h->ev_t1));
+	float ms = 0.f;
+	CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+	for (size_t e = 0; e + 1 < h->prof_used; e += 2)
+	{
+		float kms = 0.f;
+		CK(cudaEventElapsedTime(&kms, h->prof_ev[e], h->prof_ev[e + 1]));
+		h->st.step_kernel_ms += kms;
+	}
+	h->prof_used = 0;
+	h->stats_dirty = false;
+	const int n = h->window_steps > 0 ? h->window_steps : 1;
+	h->st.ms_last_call = ms;
+	h->st.ms_per_step = ms / n;
+	h->st.mlups_last_call = (double)h->st.cells * n / ((double)ms * 1e3);
+	return LUMA_B200_OK;
+}
+
+// submit deferred steps.  final = false: keep the last accepted step back (it may have to store rho,u), and on
+// launch-bound grids wait for a full CUDA-graph batch; final = true: submit everything, the last step stores rho,u.
+static int drain(luma_b200_t *h, bool final)
+{
+	int pending = h->t - h->t_enq;
+	if (pending <= 0) return LUMA_B200_OK;
+	const LumaCaseParams &p = h->p;
+	CK(cudaSetDevice(p.device));
+	const int force = force_code(p), coll = coll_code(p);
 	const int GS = h->graph_steps;
+	// Launch-bound grids (BASELINE configs[0], 256^2: ~3 us of work per step): batches of GS steps are captured once
+	// into a CUDA graph -- same kernels, same arguments, the two streams become graph branches -- and replayed with
+	// one launch each.  Only while every per-step scalar is constant (ramps finished, no time averages, no profiling
+	// events), on a single rank, and never for a step that stores rho,u.
+	const bool graph_capable = GS >= 2 && !h->ghost && !h->profiling && !h->tav;
 	auto graph_ready = [&](int t_now) -> bool
 	{
-		if (GS < 2 || h->ghost || h->profiling || h->tav) return false;
+		if (!graph_capable) return false;
 		if (velocity_ramp_coef(p, t_now * p.dt) != 1.0 || velocity_ramp_coef(p, (t_now + 1) * p.dt) != 1.0) return false;
 		if (p.reynolds_ramp_on && !((t_now + 1) * p.dt > p.reynolds_ramp)) return false;
 		return true;
 	};
+	if (!final && (pending <= 1 || (graph_ready(h->t_enq) && pending - 1 < GS))) return LUMA_B200_OK;
 
-	int s = 0;
-	while (s < nsteps)
+	StepArgs a;
+	fill_step_args(h, a);
+	if (!h->timing_open)
 	{
-		if (nsteps - s - 1 >= GS && graph_ready(h->t))
+		// a new timing window opens: the previous one is read now if it has completed, dropped otherwise
+		int rc = collect_stats(h, h->profiling);
+		if (rc) return rc;
+		h->stats_dirty = false; h->prof_used = 0;
+		CK(cudaEventRecord(h->ev_t0, h->s_main));
+		h->timing_open = true; h->timed_steps = 0;
+	}
+	CK(cudaEventRecord(h->ev_int, h->s_main));      // whatever ran on s_main since the last step (uploads, snapshots ...)
+	const int keep = final ? 0 : 1;
+	while (pending > keep)
+	{
+		if (pending - 1 >= GS && graph_ready(h->t_enq))
 		{
 			StepArgs b = a;
-			step_scalars(b, h->t);
+			step_scalars(h, b, h->t_enq);
 			GraphSlot &gs = h->graphs[h->cur];
 			if (gs.exec && (gs.omega != b.omega || gs.n_bc != h->n_bc || gs.epoch != h->geometry_epoch))
 			{
 				cudaGraphExecDestroy(gs.exec); gs.exec = nullptr;
 			}
+			int rc = join_streams(h);
+			if (rc) return rc;
 			if (!gs.exec)
 			{
 				const int64_t before = h->st.kernel_launches;
 				cudaGraph_t graph = nullptr;
 				CK(cudaStreamBeginCapture(h->s_main, cudaStreamCaptureModeRelaxed));
-				int rc = LUMA_B200_OK;
 				for (int i = 0; i < GS && rc == LUMA_B200_OK; ++i)
 				{
 					b.fin = h->f[h->cur ^ (i & 1)]; b.fout = h->f[h->cur ^ (i & 1) ^ 1];
 					b.write_macro = 0;
-					rc = enqueue_step(b);
+					rc = enqueue_step_captured(h, b, coll, force);
 				}
 				const cudaError_t ce = cudaStreamEndCapture(h->s_main, &graph);
 				gs.nodes = h->st.kernel_launches - before;
@@ -1131,22 +1257,27 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 				gs.omega = b.omega; gs.n_bc = h->n_bc; gs.epoch = h->geometry_epoch;
 			}
 			CK(cudaGraphLaunch(gs.exec, h->s_main));
+			CK(cudaEventRecord(h->ev_int, h->s_main));
 			h->st.kernel_launches += gs.nodes;
 			h->st.graph_launches++;
-			h->t += GS;       // GS is even: h->cur is unchanged
-			s += GS;
+			h->t_enq += GS;       // GS is even: h->cur is unchanged
+			h->timed_steps += GS;
+			pending -= GS;
 			continue;
 		}
-		step_scalars(a, h->t);
+		if (!final && graph_ready(h->t_enq)) break;      // fewer than a batch left: wait for more steps or for a read point
+		step_scalars(h, a, h->t_enq);
 		a.fin = h->f[h->cur]; a.fout = h->f[h->cur ^ 1];
-		a.write_macro = (s == nsteps - 1) ? 1 : 0;
+		a.write_macro = (final && pending == 1) ? 1 : 0;
 		{
-			const int rc = enqueue_step(a);
+			const int rc = enqueue_step_live(h, a, coll, force);
 			if (rc) return rc;
 		}
 		if (a.write_macro && h->n_vel)
 		{
 			// stored u of the forced-equilibrium inlet sites as the reference leaves it after this step
+			int rc = join_streams(h);
+			if (rc) return rc;
 			VelSrcArgs vs;
 			vs.list = h->vel_list; vs.n = h->n_vel; vs.types = h->types; vs.bcdesc = h->bcdesc; vs.u = h->u; vs.stride = h->stride;
 			vs.uin = h->uin; vs.ramp_t = a.ramp_t;
@@ -1154,35 +1285,71 @@ int luma_b200_step(luma_b200_t *h, int32_t nsteps)
 			LAT(h->Q, launch_velsrc<L>(vs, h->s_main, &h->st.kernel_launches));
 		}
 		h->cur ^= 1;
-		++h->t;
-		++s;
+		++h->t_enq;
+		++h->timed_steps;
+		--pending;
+		h->stepped = true;
+		if ((h->timed_steps & 63) == 0) { const int rc = halo_health(h); if (rc) return rc; }
 	}
-	if (h->ghost) CK(cudaStreamWaitEvent(h->s_main, h->ev_comm, 0));
-	CK(cudaEventRecord(h->ev_t1, h->s_main));
 	CK(cudaGetLastError());
-	CK(cudaStreamSynchronize(h->s_main));
-	if (h->p2p)
+	return LUMA_B200_OK;
+}
+
+// read point: everything accepted so far is submitted, the streams are joined into s_main and the timing window is
+// closed (ev_t1); nothing here waits for the GPU
+static int flush_steps(luma_b200_t *h)
+{
+	int rc = drain(h, true);
+	if (rc) return rc;
+	rc = join_streams(h);
+	if (rc) return rc;
+	if (h->timing_open)
 	{
-		int timed_out = 0;
-		CK(cudaMemcpy(&timed_out, h->halo_timeout, sizeof(int), cudaMemcpyDeviceToHost));
-		if (timed_out) FAIL(LUMA_B200_ENCCL, "halo exchange: a ring neighbour did not deliver its populations within 20 s");
+		CK(cudaEventRecord(h->ev_t1, h->s_main));
+		h->timing_open = false;
+		h->stats_dirty = true;
+		h->window_steps = h->timed_steps;
 	}
-	float ms = 0.f;
-	CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
-	for (size_t e = 0; e + 1 < h->prof_used; e += 2)
+	return LUMA_B200_OK;
+}
+
+int luma_b200_set_profiling(luma_b200_t *h, int32_t on)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (h->have_state)
 	{
-		float kms = 0.f;
-		CK(cudaEventElapsedTime(&kms, h->prof_ev[e], h->prof_ev[e + 1]));
-		h->st.step_kernel_ms += kms;
+		int rc = flush_steps(h);
+		if (rc == LUMA_B200_OK) rc = collect_stats(h, true);
+		if (rc) return rc;
 	}
-	h->stepped = true;
+	h->profiling = on != 0;
+	h->st.step_kernel_launches = 0; h->st.step_kernel_ms = 0.0; h->st.step_kernel_cells = 0;
+	return LUMA_B200_OK;
+}
+
+int luma_b200_step(luma_b200_t *h, int32_t nsteps)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "step before upload/init_synthetic");
+	if (nsteps < 0) FAIL(LUMA_B200_EINVAL, "nsteps < 0");
+	if (nsteps == 0) return LUMA_B200_OK;
+	int rc = halo_health(h);
+	if (rc) return rc;
+	// GridObj::t, ::omega, ::nu as the reference leaves them after these steps (optimised.cpp:39-42, :170)
+	h->t += nsteps;
+	reynolds_step(h, h->t - 1, h->omega, h->nu);
 	h->st.steps += nsteps;
-	h->st.ms_last_call = ms;
-	h->st.ms_per_step = ms / nsteps;
-	h->st.mlups_last_call = (double)h->st.cells * nsteps / ((double)ms * 1e3);
 	int plus[9];
 	h->st.halo_bytes_per_step = h->ghost ? 2LL * edge_pops(h->Q, +1, plus) * h->MK * (long long)sizeof(double) : 0;
-	return LUMA_B200_OK;
+	return drain(h, false);
+}
+
+int luma_b200_flush(luma_b200_t *h)
+{
+	if (!h) return LUMA_B200_EINVAL;
+	if (!h->have_state) return LUMA_B200_OK;
+	CK(cudaSetDevice(h->p.device));
+	return flush_steps(h);
 }
 
 int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_aos, double *rho, double *u_aos)
@@ -1194,10 +1361,12 @@ int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_ao
 		FAIL(LUMA_B200_EINVAL, "download: null array");
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
+	int rc = flush_steps(h);
+	if (rc) return rc;
 	const long long owned = (long long)p.x_count * h->MK;
 	const long long host_off = (long long)halo * h->MK, dev_off = (long long)h->ghost * h->MK;
 	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(192u << 20) / (h->Q * 8)));
-	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
+	rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
 	if (rc) return rc;
 	if (what & LUMA_B200_F)
 		for (long long c0 = 0; c0 < owned; c0 += chunk)
@@ -1219,7 +1388,7 @@ int luma_b200_download(luma_b200_t *h, int32_t halo, unsigned what, double *f_ao
 		CK(cudaMemcpyAsync(rho + host_off, h->rho + dev_off, (size_t)owned * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(h->s_main));
-	return LUMA_B200_OK;
+	return halo_health(h);
 }
 
 // Asynchronous variant for hosts that write their output while the next steps run: the requested fields
@@ -1234,6 +1403,10 @@ int luma_b200_download_async(luma_b200_t *h, int32_t halo, unsigned what, double
 		FAIL(LUMA_B200_EINVAL, "download: null array");
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
+	{
+		const int rc = flush_steps(h);
+		if (rc) return rc;
+	}
 	const long long owned = (long long)p.x_count * h->MK;
 	const long long host_off = (long long)halo * h->MK, dev_off = (long long)h->ghost * h->MK;
 	size_t need = 0;
@@ -1279,7 +1452,7 @@ int luma_b200_download_wait(luma_b200_t *h)
 	CK(cudaSetDevice(h->p.device));
 	if (h->copy_pending) CK(cudaEventSynchronize(h->ev_copied));
 	h->copy_pending = false;
-	return LUMA_B200_OK;
+	return halo_health(h);
 }
 
 // rho_timeav [cells], ui_timeav [cells*D], uiuj_timeav [cells*(3D-3)] in the reference's AoS layout (inc/GridObj.h:93-95)
@@ -1289,10 +1462,12 @@ static int transfer_timeav(luma_b200_t *h, int32_t halo, double *rho_tav, double
 	if (halo < 0 || halo > 1) FAIL(LUMA_B200_EINVAL, "timeav: halo");
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
+	int rc = flush_steps(h);
+	if (rc) return rc;
 	const long long owned = (long long)p.x_count * h->MK;
 	const long long host_off = (long long)halo * h->MK, dev_off = (long long)h->ghost * h->MK;
 	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(192u << 20) / (h->Q * 8)));
-	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
+	rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
 	if (rc) return rc;
 	if (rho_tav)
 	{
@@ -1368,9 +1543,15 @@ int luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu)
 int luma_b200_forces(luma_b200_t *h, double F[3])
 {
 	if (!h || !F) return LUMA_B200_EINVAL;
-	if (!h->have_state || !h->stepped) FAIL(LUMA_B200_ESTATE, "forces need at least one step (they use the pre-stream populations of the last step)");
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "forces before upload/init_synthetic");
 	const LumaCaseParams &p = h->p;
 	CK(cudaSetDevice(p.device));
+	int rc = flush_steps(h);
+	if (rc) return rc;
+	if (!h->stepped) FAIL(LUMA_B200_ESTATE, "forces need at least one step (they use the pre-stream populations of the last step)");
+	// Every link is summed by the rank that owns its FLUID end: the populations read are those of this rank's own
+	// planes of the previous lattice, which nobody else writes (a ring neighbour that is already one step ahead
+	// stores into the GHOST planes of that lattice); the solid end may lie in a ghost plane (eType is static).
 	const double *prev = h->f[h->cur ^ 1];
 	int nb;
 	LAT(h->Q, nb = launch_momex<L>(prev, h->types, h->stride, h->P, p.M, p.K, h->ghost, h->P - h->ghost, p.x_offset - h->ghost, p.N, h->momex_dev, 4096, h->s_main));
@@ -1381,12 +1562,22 @@ int luma_b200_forces(luma_b200_t *h, double F[3])
 	CK(cudaStreamSynchronize(h->s_main));
 	F[0] = F[1] = F[2] = 0.0;
 	for (int b = 0; b < nb; ++b) { F[0] += part[3 * b]; F[1] += part[3 * b + 1]; F[2] += part[3 * b + 2]; }
-	return LUMA_B200_OK;
+	return halo_health(h);
 }
 
 int luma_b200_stats(luma_b200_t *h, LumaStats *s)
 {
 	if (!h || !s) return LUMA_B200_EINVAL;
+	if (h->have_state)
+	{
+		// a read point: what is still deferred is submitted, then the device time of the steps since the previous
+		// read point is collected (this is the one place that waits for them)
+		CK(cudaSetDevice(h->p.device));
+		int rc = flush_steps(h);
+		if (rc == LUMA_B200_OK) rc = collect_stats(h, true);
+		if (rc == LUMA_B200_OK) rc = halo_health(h);
+		if (rc) return rc;
+	}
 	*s = h->st;
 	return LUMA_B200_OK;
 }
@@ -1426,11 +1617,16 @@ int luma_b200_sync(luma_b200_t *h)
 {
 	if (!h) return LUMA_B200_EINVAL;
 	CK(cudaSetDevice(h->p.device));
+	if (h->have_state)
+	{
+		const int rc = flush_steps(h);
+		if (rc) return rc;
+	}
 	CK(cudaStreamSynchronize(h->s_main));
 	CK(cudaStreamSynchronize(h->s_comm));
 	CK(cudaStreamSynchronize(h->s_copy));
 	h->copy_pending = false;
-	return LUMA_B200_OK;
+	return halo_health(h);
 }
 
 }  // extern "C"

@@ -26,8 +26,8 @@ struct StepArgs
 	double lam[4];            // (1 - 0.5*omega) * (w/(cs*cs)) per weight class            optimised.cpp:962
 	double kbc_beta_m1;       // 2.0 / omega                                               optimised.cpp:1279
 	double kbc_inv_beta;      // 1.0 / kbc_beta_m1                                         optimised.cpp:1293
-	double F[3];              // force_xyz (uniform: rho_init * gravity along one axis)    init_grids.cpp:296
-	double hF[3];             // 0.5 * F
+	double Fg;                // force_xyz along L_GRAVITY_DIRECTION (uniform: rho_init * gravity; the other components are 0) init_grids.cpp:296
+	double hFg;               // 0.5 * Fg
 	LbmConst C;
 	// boundary sites
 	const long long *bc_list; // local site ids of the sites k_bc handles (classes 2, 3, 4), ascending
@@ -114,11 +114,11 @@ struct SynthArgs
 	LbmConst C;
 };
 
-// coll: 0 BGK, 1 BGK + Smagorinsky, 2 KBC (D2Q9 and D3Q27 only; D3Q27 always)
-template <class L> void launch_step(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches);
-template <class L> void launch_bc(const StepArgs &a, int coll, bool force, cudaStream_t s, int64_t *launches);
+// coll: 0 BGK, 1 BGK + Smagorinsky, 2 KBC (D2Q9 and D3Q27 only; D3Q27 always); force: 0 none, 1 + L_GRAVITY_DIRECTION
+template <class L> void launch_step(const StepArgs &a, int coll, int force, int nplanes, cudaStream_t s, int64_t *launches);
+template <class L> void launch_bc(const StepArgs &a, int coll, int force, cudaStream_t s, int64_t *launches);
 // k_step on the slab's face planes that also stores the outgoing populations into the neighbours' ghost planes (a.peer_f)
-template <class L> void launch_step_faces(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches);
+template <class L> void launch_step_faces(const StepArgs &a, int coll, int force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
 void launch_halo_push(const HaloPushArgs &a, cudaStream_t s);
 void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s);
@@ -127,6 +127,9 @@ void launch_force_general(uint32_t *cw, const long long *ids, int n, int class_s
 void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);
+// f = feq(rho, u) on sites [first, first + n): LBM_initGrid's population initialisation (init_grids.cpp:310-333)
+template <class L> void launch_feq_init(const double *rho, const double *u, double *f, long long stride, long long first, long long n,
+	const LbmConst &C, cudaStream_t s);
 template <class L> void launch_aos_to_soa(const double *aos, double *soa, long long stride, long long first_cell, long long ncells, cudaStream_t s);
 template <class L> void launch_soa_to_aos(const double *soa, double *aos, long long stride, long long first_cell, long long ncells, cudaStream_t s);
 // vectors of ncomp = 2, 3 or 6 components per site (u, ui_timeav, uiuj_timeav)

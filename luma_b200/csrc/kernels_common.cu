@@ -82,10 +82,13 @@ void launch_halo_push(const HaloPushArgs &a, cudaStream_t s)
 }
 
 // thread 0 waits for the left neighbour's data, thread 1 for the right neighbour's; gives up after
-// 20 s (a dead peer must not hang the GPU) and reports it through *timed_out
+// 20 s (a dead peer must not hang the GPU) and reports it through *timed_out, a word in mapped host memory that
+// the host polls.  Once it is set every later wait returns at once: the queued steps drain in microseconds
+// (on stale ghost planes -- the call that notices the flag returns LUMA_B200_ENCCL and the state is void).
 __global__ void k_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out)
 {
 	if (threadIdx.x > 1) return;
+	if (*reinterpret_cast<volatile int *>(timed_out) != 0) return;
 	unsigned long long t0, t1, seen;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 	for (;;)
@@ -94,7 +97,7 @@ __global__ void k_halo_wait(const unsigned long long *flags, unsigned long long 
 		if (seen >= value) break;
 		__nanosleep(64);
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-		if (t1 - t0 > 20000000000ull) { *timed_out = 1; break; }
+		if (t1 - t0 > 20000000000ull) { *reinterpret_cast<volatile int *>(timed_out) = 1; __threadfence_system(); break; }
 	}
 }
 

@@ -133,14 +133,14 @@ __device__ __forceinline__ void load_own(const StepArgs &a, const long long id, 
 
 // BGK(/Smagorinsky) collision with optional Guo forcing, GridObj::_LBM_collide_opt (optimised.cpp:765-790),
 // or the KBC operator _LBM_kbcCollide_opt (:1122-1305), which replaces f by the collided own-site populations
-template <class L, int COLL, bool FORCE>
+template <class L, int COLL, int FORCE>
 __device__ __forceinline__ void collide(const StepArgs &a, const long long id, const double (&u)[3], const double (&feq)[L::Q], double (&f)[L::Q])
 {
 	if constexpr (COLL == COLL_KBC)
 	{
 		double fo[L::Q];
 		load_own<L>(a, id, fo);
-		kbc_collide<L, FORCE>(u, feq, fo, a.kbc_beta_m1, a.kbc_inv_beta, a.F, a.C, a.lam, f);
+		kbc_collide<L, FORCE>(u, feq, fo, a.kbc_beta_m1, a.kbc_inv_beta, a.Fg, a.C, a.lam, f);
 		return;
 	}
 	double omega_s = a.omega;
@@ -148,8 +148,8 @@ __device__ __forceinline__ void collide(const StepArgs &a, const long long id, c
 #pragma unroll
 	for (int v = 0; v < L::Q; ++v)
 	{
-		if (FORCE)
-			f[v] = f[v] + (omega_s * (feq[v] - f[v]) + guo_force<L>(v, u, a.F, a.C, a.lam));
+		if constexpr (FORCE != 0)
+			f[v] = f[v] + (omega_s * (feq[v] - f[v]) + guo_force<L, (FORCE > 0 ? FORCE - 1 : 0)>(v, u, a.Fg, a.C, a.lam));
 		else
 			f[v] = f[v] + omega_s * (feq[v] - f[v]);
 	}
@@ -299,7 +299,7 @@ __device__ __forceinline__ void tavg_update(const StepArgs &a, const long long i
 // ------------------------------------------------------------------------------------------------
 // the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
 // ------------------------------------------------------------------------------------------------
-template <class L, int COLL, bool FORCE, bool TAVG, bool PEER>
+template <class L, int COLL, int FORCE, bool TAVG, bool PEER>
 __device__ __forceinline__ void step_site(const StepArgs &a)
 {
 	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
@@ -311,7 +311,7 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 
 	double f[L::Q], feq[L::Q], u[3], rho;
 	pull_populations<L>(a, p, r, id, w, f);
-	macroscopic<L, FORCE>(f, a.hF, rho, u);
+	macroscopic<L, FORCE>(f, a.hFg, rho, u);
 	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
 	equilibrium_all<L>(rho, u, a.C, feq);
 	collide<L, COLL, FORCE>(a, id, u, feq, f);
@@ -325,7 +325,7 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 	}
 }
 
-template <class L, int COLL, bool FORCE, bool TAVG>
+template <class L, int COLL, int FORCE, bool TAVG>
 __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_step(const StepArgs a)
 {
 	step_site<L, COLL, FORCE, TAVG, false>(a);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_st
 
 // the same on the two face planes of a slab, with the outgoing populations also stored into the neighbours' ghost
 // planes (fused halo exchange; two planes per step, so its occupancy is irrelevant)
-template <class L, int COLL, bool FORCE, bool TAVG>
+template <class L, int COLL, int FORCE, bool TAVG>
 __global__ void __launch_bounds__(STEP_THREADS) k_step_faces(const StepArgs a)
 {
 	step_site<L, COLL, FORCE, TAVG, true>(a);
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step_faces(const StepArgs a)
 // new-time rho,u of an extrapolation neighbour: GridObj::_LBM_updateAndExtrapolate +
 // _LBM_updateInteriorLatticeSite (optimised.cpp:1353-1434).  A fluid neighbour is streamed and
 // "macro'd" from the old lattice here; any other type keeps its stored values (its macro is a no-op).
-template <class L, bool FORCE>
+template <class L, int FORCE>
 __device__ __noinline__ void neighbour_macro(const StepArgs &a, const int p, const int j, const int k, double &rho, double (&u)[3])
 {
 	const unsigned r = (unsigned)j * (unsigned)a.K + (unsigned)k;
@@ -353,7 +353,7 @@ __device__ __noinline__ void neighbour_macro(const StepArgs &a, const int p, con
 	{
 		double f[L::Q];
 		pull_any<L>(a, p, r, j, k, id, w, f);
-		macroscopic<L, FORCE>(f, a.hF, rho, u);
+		macroscopic<L, FORCE>(f, a.hFg, rho, u);
 	}
 	else
 	{
@@ -375,7 +375,7 @@ __device__ __forceinline__ bool bc_needs_neighbours(const uint32_t w)
 	return (w >> CW_EC_SHIFT) > 1u || cw_class<L>(w) == CLS_PRESSURE;
 }
 
-template <class L, int COLL, bool FORCE>
+template <class L, int COLL, int FORCE>
 __device__ __forceinline__ void bc_regularise(const StepArgs &a, const long long id, const uint32_t w, const int j, double (&f)[L::Q],
 	const double r1, const double (&u1)[3], const double r2, const double (&u2)[3], double &dens, double (&uw)[3])
 {
@@ -479,14 +479,14 @@ __device__ __forceinline__ void bc_regularise(const StepArgs &a, const long long
 
 // class-4 sites: stream per link, macro only for eFluid/eSlip (optimised.cpp:803-806; every other type
 // keeps its stored rho,u), force, collide
-template <class L, int COLL, bool FORCE, bool TAVG>
+template <class L, int COLL, int FORCE, bool TAVG>
 __device__ __noinline__ void general_site(const StepArgs &a, const int p, const int j, const int k, const long long id,
 	const uint32_t w, const int reps)
 {
 	const uint8_t type = a.types[id];
 	double f[L::Q], feq[L::Q], u[3], rho;
 	pull_general<L>(a, p, j, k, id, site_desc<L>(a, id, w), type, f);
-	if (type == T_FLUID || type == T_SLIP) macroscopic<L, FORCE>(f, a.hF, rho, u);
+	if (type == T_FLUID || type == T_SLIP) macroscopic<L, FORCE>(f, a.hFg, rho, u);
 	else
 	{
 		rho = a.rho[id];
@@ -503,7 +503,7 @@ __device__ __noinline__ void general_site(const StepArgs &a, const int p, const 
 	for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
 }
 
-template <class L, int COLL, bool FORCE, bool TAVG>
+template <class L, int COLL, int FORCE, bool TAVG>
 __global__ void __launch_bounds__(64) k_bc(const StepArgs a)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -607,14 +607,21 @@ template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64
 #ifdef __CUDACC__   // launchers: <<<>>> needs nvcc (tests/harness compiles the kernels above for the host)
 // kernel variant = collision operator x Guo forcing x time averages; the reference ties KBC to D2Q9 / D3Q27 and
 // D3Q27 to KBC (inc/definitions.h:299-310), so only those combinations are instantiated
+#define LUMA_DISPATCH_T(KERNEL, COLL, FORCE_, GRID, THREADS) \
+	do { \
+		if (a.tav) KERNEL<L, COLL, FORCE_, true><<<GRID, THREADS, 0, s>>>(a); \
+		else KERNEL<L, COLL, FORCE_, false><<<GRID, THREADS, 0, s>>>(a); \
+	} while (0)
+// force: 0 = none, 1 + L_GRAVITY_DIRECTION otherwise (the direction is a template argument: the zero components of
+// force_xyz vanish at compile time)
 #define LUMA_DISPATCH_FT(KERNEL, COLL, GRID, THREADS) \
 	do { \
-		switch ((force ? 2 : 0) | (a.tav ? 1 : 0)) \
+		switch (force) \
 		{ \
-		case 0: KERNEL<L, COLL, false, false><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 1: KERNEL<L, COLL, false, true><<<GRID, THREADS, 0, s>>>(a); break; \
-		case 2: KERNEL<L, COLL, true, false><<<GRID, THREADS, 0, s>>>(a); break; \
-		default: KERNEL<L, COLL, true, true><<<GRID, THREADS, 0, s>>>(a); break; \
+		case 0: LUMA_DISPATCH_T(KERNEL, COLL, 0, GRID, THREADS); break; \
+		case 1: LUMA_DISPATCH_T(KERNEL, COLL, 1, GRID, THREADS); break; \
+		case 2: LUMA_DISPATCH_T(KERNEL, COLL, 2, GRID, THREADS); break; \
+		default: if constexpr (L::D == 3) { LUMA_DISPATCH_T(KERNEL, COLL, 3, GRID, THREADS); } break; \
 		} \
 	} while (0)
 #define LUMA_DISPATCH(KERNEL, GRID, THREADS) \
@@ -625,7 +632,7 @@ template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64
 		else { LUMA_DISPATCH_FT(KERNEL, COLL_BGK, GRID, THREADS); } \
 	} while (0)
 
-template <class L> void launch_step(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches)
+template <class L> void launch_step(const StepArgs &a, int coll, int force, int nplanes, cudaStream_t s, int64_t *launches)
 {
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
@@ -633,7 +640,7 @@ template <class L> void launch_step(const StepArgs &a, int coll, bool force, int
 	if (launches) ++*launches;
 }
 
-template <class L> void launch_step_faces(const StepArgs &a, int coll, bool force, int nplanes, cudaStream_t s, int64_t *launches)
+template <class L> void launch_step_faces(const StepArgs &a, int coll, int force, int nplanes, cudaStream_t s, int64_t *launches)
 {
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
@@ -641,7 +648,7 @@ template <class L> void launch_step_faces(const StepArgs &a, int coll, bool forc
 	if (launches) ++*launches;
 }
 
-template <class L> void launch_bc(const StepArgs &a, int coll, bool force, cudaStream_t s, int64_t *launches)
+template <class L> void launch_bc(const StepArgs &a, int coll, int force, cudaStream_t s, int64_t *launches)
 {
 	if (a.n_bc <= 0) return;
 	const int threads = 64;
@@ -785,6 +792,34 @@ template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s)
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// f = feq(rho, u) at every site of a plane range: the population initialisation of LBM_initGrid
+// (src/GridObj_init_grids.cpp:310-333) on the device, for hosts that hand over rho, u and LatTyp of a
+// freshly initialised grid (t = 0) and keep the 19 x 8 B per site of f off the PCIe bus.
+// ------------------------------------------------------------------------------------------------
+template <class L>
+__global__ void __launch_bounds__(128) k_feq_init(const double *__restrict__ rho, const double *__restrict__ u, double *__restrict__ f,
+	const long long stride, const long long first, const long long n, const LbmConst C)
+{
+	const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	const long long id = first + s;
+	double uu[3] = { 0.0, 0.0, 0.0 }, feq[L::Q];
+#pragma unroll
+	for (int d = 0; d < L::D; ++d) uu[d] = u[(long long)d * stride + id];
+	equilibrium_all<L>(rho[id], uu, C, feq);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v) f[(long long)v * stride + id] = feq[v];
+}
+
+#ifdef __CUDACC__
+template <class L> void launch_feq_init(const double *rho, const double *u, double *f, long long stride, long long first, long long n,
+	const LbmConst &C, cudaStream_t s)
+{
+	if (n > 0) k_feq_init<L><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(rho, u, f, stride, first, n, C);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // layout conversion between LUMA's AoS (inc/IVector.h:94-134) and the device SoA
 // ------------------------------------------------------------------------------------------------
 template <int Q>
@@ -832,6 +867,10 @@ template <class L> void launch_soa_to_aos(const double *soa, double *aos, long l
 // momentum exchange on eSolid sites, ObjectManager::computeLiftDrag(i,j,k,g)
 // (src/ObjectManager.cpp:93-164): for every link n of a solid site whose far end (site - c_opp(n))
 // is on the grid and eFluid, add 2 c_opp f_opp(far end), f = populations BEFORE the step.
+// Slabs: a link is summed by the rank that OWNS ITS FLUID END -- the solid end may lie in a ghost plane (eType of
+// the ghost planes is exchanged once, with the geometry), the populations read are always those of owned planes.
+// No ghost-plane population is read, so a ring neighbour that already runs the next step (and stores into the
+// ghost planes of the lattice read here) cannot race with this kernel.
 // Summation order here: per-thread over n ascending, fixed-shape tree over the block, then the
 // host adds the per-block partials in block order (deterministic; differs from the reference's
 // serial i,j,k order, hence a tolerance in the tests).
@@ -841,23 +880,25 @@ __global__ void __launch_bounds__(256) k_momex(const double *__restrict__ f, con
 	int P, int M, int K, int p_begin, int p_end, int x_first, int N, double *__restrict__ partials)
 {
 	const long long MK = (long long)M * K;
-	const long long total = (long long)(p_end - p_begin) * MK;
+	const long long total = (long long)P * MK;
 	double F0 = 0.0, F1 = 0.0, F2 = 0.0;
 	for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x)
 	{
-		const int p = p_begin + (int)(s / MK);
-		const long long r = s - (long long)(p - p_begin) * MK;
+		const int p = (int)(s / MK);
+		const long long r = s - (long long)p * MK;
 		const int j = (int)(r / K), k = (int)(r - (long long)j * K);
-		const long long id = (long long)p * MK + r;
-		if (types[id] != 0) continue;
 		const int gi = x_first + p;
+		if (gi < 0 || gi >= N) continue;      // ghost plane beyond the grid (the periodic image: no momentum exchange across the wrap)
+		if (types[s] != 0) continue;
 #pragma unroll
 		for (int n = 0; n < L::Q; ++n)
 		{
 			const int no = opposite<L>(n);
 			const int xd = gi - L::c(no, 0), yd = j - L::c(no, 1), zd = k - L::c(no, 2);
 			if (xd < 0 || xd >= N || yd < 0 || yd >= M || zd < 0 || zd >= K) continue;
-			const long long dest = ((long long)(p - L::c(no, 0)) * M + yd) * K + zd;
+			const int dp = p - L::c(no, 0);
+			if (dp < p_begin || dp >= p_end) continue;      // the fluid end belongs to another rank
+			const long long dest = ((long long)dp * M + yd) * K + zd;
 			if (types[dest] != 1) continue;
 			const double fv = f[(long long)no * stride + dest];
 			F0 += 2.0 * (double)L::c(no, 0) * fv;
@@ -890,7 +931,7 @@ __global__ void __launch_bounds__(256) k_momex(const double *__restrict__ f, con
 template <class L> int launch_momex(const double *f_prev, const uint8_t *types, long long stride, int P, int M, int K,
 	int p_begin, int p_end, int x_first, int N, double *partials, int max_blocks, cudaStream_t s)
 {
-	const long long total = (long long)(p_end - p_begin) * M * K;
+	const long long total = (long long)P * M * K;
 	int blocks = (int)((total + 255) / 256);
 	if (blocks > max_blocks) blocks = max_blocks;
 	if (blocks < 1) blocks = 1;
@@ -901,12 +942,13 @@ template <class L> int launch_momex(const double *f_prev, const uint8_t *types, 
 
 // explicit instantiations
 #define LUMA_INST(L) \
-	template void launch_step<L>(const StepArgs &, int, bool, int, cudaStream_t, int64_t *); \
-	template void launch_bc<L>(const StepArgs &, int, bool, cudaStream_t, int64_t *); \
-	template void launch_step_faces<L>(const StepArgs &, int, bool, int, cudaStream_t, int64_t *); \
+	template void launch_step<L>(const StepArgs &, int, int, int, cudaStream_t, int64_t *); \
+	template void launch_bc<L>(const StepArgs &, int, int, cudaStream_t, int64_t *); \
+	template void launch_step_faces<L>(const StepArgs &, int, int, int, cudaStream_t, int64_t *); \
 	template void launch_velsrc<L>(const VelSrcArgs &, cudaStream_t, int64_t *); \
 	template void launch_cell_words<L>(const GeomArgs &, cudaStream_t); \
 	template void launch_synthetic<L>(const SynthArgs &, cudaStream_t); \
+	template void launch_feq_init<L>(const double *, const double *, double *, long long, long long, long long, const LbmConst &, cudaStream_t); \
 	template void launch_aos_to_soa<L>(const double *, double *, long long, long long, long long, cudaStream_t); \
 	template void launch_soa_to_aos<L>(const double *, double *, long long, long long, long long, cudaStream_t); \
 	template int launch_momex<L>(const double *, const uint8_t *, long long, int, int, int, int, int, int, int, double *, int, cudaStream_t);

@@ -150,6 +150,21 @@ __host__ __device__ inline uint32_t cw_pack_bc(int ec, int nd, int nx, int ny, i
 		((uint32_t)((nx + 1) | ((ny + 1) << 2) | ((nz + 1) << 4)) << CW_N_SHIFT);
 }
 
+// ---- c_v . u in the reference's term order (d = 0, 1, 2), components with c = 0 dropped.  Used for A of the
+//      equilibrium and for beta of the Guo force: one expression tree, so the compiler keeps one copy.  For the
+//      opposite direction the value is the exact negative (IEEE rounding is sign-symmetric). ----
+template <class L>
+__device__ __forceinline__ double dir_dot(const int v, const double (&u)[3])
+{
+	const int c0 = L::c(v, 0), c1 = L::c(v, 1), c2 = L::c(v, 2);
+	double A = 0.0;
+	bool first = true;
+	if (c0 != 0) { A = (c0 > 0) ? u[0] : -u[0]; first = false; }
+	if (c1 != 0) { const double t = (c1 > 0) ? u[1] : -u[1]; A = first ? t : A + t; first = false; }
+	if (L::D == 3 && c2 != 0) { const double t = (c2 > 0) ? u[2] : -u[2]; A = first ? t : A + t; first = false; }
+	return A;
+}
+
 // ---- equilibrium for all Q directions, GridObj::_LBM_equilibrium_opt (optimised.cpp:674-705):
 //        feq = rho * w[v] * (1.0 + (A / SQ(cs)) + (B / (2.0 * SQ(cs) * SQ(cs))))
 //      evaluated per opposite pair: A(opp) = -A and B(opp) = B hold exactly in IEEE arithmetic. ----
@@ -176,11 +191,7 @@ __device__ __forceinline__ void equilibrium_all(const double rho, const double (
 	for (int v = 0; v < L::Q - 1; v += 2)
 	{
 		const int c0 = L::c(v, 0), c1 = L::c(v, 1), c2 = L::c(v, 2);
-		double A = 0.0;
-		bool first = true;
-		if (c0 != 0) { A = (c0 > 0) ? u[0] : -u[0]; first = false; }
-		if (c1 != 0) { const double t = (c1 > 0) ? u[1] : -u[1]; A = first ? t : A + t; first = false; }
-		if (L::D == 3 && c2 != 0) { const double t = (c2 > 0) ? u[2] : -u[2]; A = first ? t : A + t; first = false; }
+		const double A = dir_dot<L>(v, u);
 		double B = (c0 ? t1[0] : t0[0]) + (c1 ? t1[1] : t0[1]);
 		if (L::D == 3) B = B + (c2 ? t1[2] : t0[2]);
 		if (c0 * c1 != 0) B = B + ((c0 * c1 > 0) ? x01 : -x01);
@@ -200,9 +211,12 @@ __device__ __forceinline__ void equilibrium_all(const double rho, const double (
 	}
 }
 
-// ---- rho = sum f, rho*u = sum c f (+ F/2), GridObj::_LBM_macro_opt (optimised.cpp:800-847) ----
-template <class L, bool FORCE>
-__device__ __forceinline__ void macroscopic(const double (&f)[L::Q], const double (&hF)[3], double &rho, double (&u)[3])
+// ---- rho = sum f, rho*u = sum c f (+ F/2), GridObj::_LBM_macro_opt (optimised.cpp:800-847).
+//      FORCE = 0: no body force; FORCE = 1 + L_GRAVITY_DIRECTION otherwise.  force_xyz is uniform and has ONE non-zero
+//      component (rho_init * gravity along the gravity direction, src/GridObj_init_grids.cpp:296-297), so the other
+//      two additions of the reference add +0.0 to a sum that is never -0.0 and are dropped. ----
+template <class L, int FORCE>
+__device__ __forceinline__ void macroscopic(const double (&f)[L::Q], const double hFg, double &rho, double (&u)[3])
 {
 	double r = f[0];
 	double m[3] = { 0.0, 0.0, 0.0 };
@@ -223,12 +237,9 @@ __device__ __forceinline__ void macroscopic(const double (&f)[L::Q], const doubl
 			}
 		}
 	}
-	if (FORCE)
-	{
-		m[0] = m[0] + hF[0];
-		m[1] = m[1] + hF[1];
-		if (L::D == 3) m[0] = m[0] + hF[2];   // sic: the reference adds F_z/2 to the x momentum (optimised.cpp:833)
-	}
+	if (FORCE == 1) m[0] = m[0] + hFg;
+	if (FORCE == 2) m[1] = m[1] + hFg;
+	if (FORCE == 3 && L::D == 3) m[0] = m[0] + hFg;   // sic: the reference adds F_z/2 to the x momentum (optimised.cpp:833)
 	rho = r;
 	u[0] = m[0] / r;
 	u[1] = m[1] / r;
@@ -278,18 +289,28 @@ __device__ __forceinline__ double smagorinsky_omega(const double (&f)[L::Q], con
 	return 1.0 / (tau + tau_t);
 }
 
-// ---- Guo forcing term of one direction, GridObj::_LBM_forceGrid_opt (optimised.cpp:959-989) ----
-template <class L>
-__device__ __forceinline__ double guo_force(const int v, const double (&u)[3], const double (&F)[3], const LbmConst &C, const double (&lam)[4])
+// ---- Guo forcing term of one direction, GridObj::_LBM_forceGrid_opt (optimised.cpp:959-989):
+//        beta = (sum_d c_d u_d) * (1/cs^2);   F_v = (sum_d F_d * (c_d * (1 + beta) - u_d)) * lambda_v
+//      G = L_GRAVITY_DIRECTION, the one direction in which force_xyz is non-zero (Fg); the terms of the other
+//      directions are (+-0) added to a running sum and cannot change it, so
+//        F_v = (Fg * (c_G * (1 + beta) - u_G)) * lambda_v
+//      with c_G * (1 + beta) = +-(1 + beta) or +0.  beta of the odd member of an opposite pair is the exact negative
+//      of the even member's, 1.0 + (-b) == 1.0 - b; directions with c_G = 0 share one value per weight class
+//      (the compiler folds the repeated expressions of the unrolled loop).  Was: 2 dot products per direction. ----
+template <class L, int G>
+__device__ __forceinline__ double guo_force(const int v, const double (&u)[3], const double Fg, const LbmConst &C, const double (&lam)[4])
 {
-	double beta = 0.0;
-#pragma unroll
-	for (int d = 0; d < L::D; ++d) beta = beta + ((double)L::c(v, d) * u[d]);
-	beta = beta * C.inv_cs2;
-	double fi = 0.0;
-#pragma unroll
-	for (int d = 0; d < L::D; ++d) fi = fi + F[d] * ((double)L::c(v, d) * (1.0 + beta) - u[d]);
-	return fi * lam[L::wclass(v)];
+	const int cg = L::c(v, G);
+	double term;
+	if (cg == 0) term = 0.0 - u[G];
+	else
+	{
+		const int ve = v & ~1;      // cg != 0 rules out the rest population: ve, ve + 1 are an opposite pair
+		const double b = dir_dot<L>(ve, u) * C.inv_cs2;
+		const double p = (v == ve) ? 1.0 + b : 1.0 - b;
+		term = (cg > 0) ? p - u[G] : (-p) - u[G];
+	}
+	return (Fg * term) * lam[L::wclass(v)];
 }
 
 // ---- KBC collision, GridObj::_LBM_kbcCollide_opt (optimised.cpp:1122-1305): KBC-D on D2Q9, KBC-N4 on
@@ -305,9 +326,9 @@ template <class L> __host__ __device__ constexpr int kbc_coef(int v, int m)
 	return L::c(v, a) * L::c(v, b) * (t < 0 ? 1 : L::c(v, t));
 }
 
-template <class L, bool FORCE>
+template <class L, int FORCE>
 __device__ __forceinline__ void kbc_collide(const double (&u)[3], const double (&feq)[L::Q], const double (&fo)[L::Q],
-	const double beta_m1, const double inv_beta, const double (&F)[3], const LbmConst &C, const double (&lam)[4], double (&out)[L::Q])
+	const double beta_m1, const double inv_beta, const double Fg, const LbmConst &C, const double (&lam)[4], double (&out)[L::Q])
 {
 	constexpr int NM = (L::D == 3) ? 13 : 3;
 	double M[NM], fneq[L::Q], ds[L::Q], dh[L::Q];
@@ -390,7 +411,7 @@ __device__ __forceinline__ void kbc_collide(const double (&u)[3], const double (
 #pragma unroll
 	for (int v = 0; v < L::Q; ++v)
 	{
-		if (FORCE) out[v] = fo[v] - inv_beta * (2.0 * ds[v] + gamma * dh[v]) + guo_force<L>(v, u, F, C, lam);
+		if constexpr (FORCE != 0) out[v] = fo[v] - inv_beta * (2.0 * ds[v] + gamma * dh[v]) + guo_force<L, (FORCE > 0 ? FORCE - 1 : 0)>(v, u, Fg, C, lam);
 		else out[v] = fo[v] - inv_beta * (2.0 * ds[v] + gamma * dh[v]);
 	}
 }

@@ -105,12 +105,13 @@ class GridObj:
         """Hand over the host state of an existing LUMA GridObj (AoS arrays covering this rank's planes,
         plus `halo` planes each side).  `bc_sites`: iterable of (site, edge_count, normal_dir, (nx,ny,nz));
         by default computed from the case's wall thicknesses like GridUtils::isWithinDomainWall."""
-        f = np.ascontiguousarray(f, dtype=np.float64)
+        # f=None: the host declares f = feq(rho,u) everywhere (LBM_initGrid's state at t = 0); nothing is uploaded for it
+        f = None if f is None else np.ascontiguousarray(f, dtype=np.float64)
         rho = np.ascontiguousarray(rho, dtype=np.float64)
         u = np.ascontiguousarray(u, dtype=np.float64)
         lt = np.ascontiguousarray(LatTyp, dtype=np.int32)
         ncell = (self.x_count + 2 * halo) * self.M_lim * self.K_lim
-        if f.size != ncell * self.Q or rho.size != ncell or u.size != ncell * self.D or lt.size != ncell:
+        if (f is not None and f.size != ncell * self.Q) or rho.size != ncell or u.size != ncell * self.D or lt.size != ncell:
             raise ValueError("upload: array sizes do not match the local grid")
         if bc_sites is None:
             bc_sites = self.defs.boundary_site_descriptors(lt, x_offset=self.x_offset - halo)
@@ -128,7 +129,12 @@ class GridObj:
 
     # ---- the time step ----
     def LBM_multi_opt(self, nsteps: int = 1):
+        """Accepts `nsteps` time steps; never waits for the GPU (see luma_b200_step in include/luma_b200.h)."""
         capi.check(self._L.luma_b200_step(self._h, int(nsteps)), self._h)
+
+    def flush(self):
+        """Submit every accepted step to the GPU without reading anything back or waiting."""
+        capi.check(self._L.luma_b200_flush(self._h), self._h)
 
     # ---- scalars the reference keeps on the object ----
     def _time(self):

@@ -51,13 +51,37 @@ def broadcast_unique_id(dist, rank: int, make_id: Optional[Callable[[], bytes]] 
     return bytes(uid)
 
 
-def attach_p2p(dist, grid, rank: int, nranks: int):
+def attach_p2p(dist, grid, rank: int, nranks: int) -> bool:
     """All-gather the ranks' IPC blobs and hand `grid` those of its ring neighbours (MPI_Allgather in a LUMA
-    MPI build): from then on its halo exchange is device-initiated (include/luma_b200.h)."""
+    MPI build): from then on its halo exchange is device-initiated (include/luma_b200.h).
+
+    The decision is COLLECTIVE: peer stores are used only if every rank could export its blob.  Attaching itself
+    is then tried on all ranks and the outcomes are agreed on with a second reduction; a rank whose neighbours
+    attached while it could not would leave the ring with mixed transports (one side waiting for flags the other
+    never writes), so in that case every rank raises.  Returns True when the ring runs on peer stores, False when
+    all ranks stay on the NCCL exchange."""
+    try:
+        blob = grid.p2p_export()
+    except Exception:
+        blob = b""
     blobs = [None] * nranks
-    dist.all_gather_object(blobs, grid.p2p_export())
-    grid.p2p_attach(blobs[(rank - 1) % nranks], blobs[(rank + 1) % nranks])
-    return grid
+    dist.all_gather_object(blobs, blob)
+    if not all(isinstance(b, (bytes, bytearray)) and len(b) == 256 for b in blobs):
+        return False                    # same list on every rank: everybody stays on NCCL
+    ok = 1
+    err = None
+    try:
+        grid.p2p_attach(blobs[(rank - 1) % nranks], blobs[(rank + 1) % nranks])
+    except Exception as ex:             # e.g. no peer access between two GPUs of the box
+        ok, err = 0, ex
+    flags = [None] * nranks
+    dist.all_gather_object(flags, ok)
+    if all(flags):
+        return True
+    if not any(flags):
+        return False                    # nobody attached: NCCL everywhere
+    raise RuntimeError("p2p_attach succeeded on ranks %s only (%r): recreate the handles and use the NCCL exchange"
+                       % ([r for r, f in enumerate(flags) if f], err))
 
 
 def execute_plan_on_host(dist, plan: List[dict], lattice):

@@ -40,7 +40,9 @@
 #ifndef L_GRID_OUT_FREQ
 #define L_GRID_OUT_FREQ 1000000000
 #endif
+#ifndef L_EXTRA_OUT_FREQ
 #define L_EXTRA_OUT_FREQ 1000000000
+#endif
 #define L_OUTPUT_PRECISION 17
 #define L_RESTART_OUT_FREQ 1000000000
 #define L_PROBE_OUT_FREQ 1000000000

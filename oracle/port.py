@@ -250,17 +250,18 @@ def _read_kv(path):
     return out
 
 
-def run_ref_dump(name: str, steps, outdir=None):
-    """Run the compiled reference for `steps` (ascending) and return {tag: {array name: ndarray}}."""
-    exe = ref_binary(name)
+def run_ref_dump(name: str, steps, outdir=None, omp: bool = False, threads=None):
+    """Run the compiled reference for `steps` (ascending) and return {tag: {array name: ndarray}}.
+    omp=True uses the OpenMP build (bit-identical results: every site is updated from the old lattice only)."""
+    exe = ref_binary(name, omp=omp)
     if exe is None:
-        raise FileNotFoundError("oracle/_ref/luma_ref_%s not built (make -C oracle ref)" % name)
+        raise FileNotFoundError("oracle/_ref/luma_ref_%s%s not built (make -C oracle ref)" % (name, "_omp" if omp else ""))
     own = outdir is None
     if own:
         tmp = tempfile.TemporaryDirectory(prefix="luma_ref_")
         outdir = tmp.name
     subprocess.run([exe, "dump", outdir, ",".join(str(int(s)) for s in steps)], check=True,
-                   env=dict(os.environ, OMP_NUM_THREADS="1"))
+                   env=dict(os.environ, OMP_NUM_THREADS=str(int(threads or os.cpu_count() or 1)) if omp else "1"))
     res = {}
     for tag in ["init"] + ["t%d" % s for s in steps]:
         d = {}

@@ -23,6 +23,10 @@
 #include "LUMA/inc/ObjectManager.h"
 #include "LUMA/inc/PCpts.h"
 
+#ifdef LUMA_DROPIN
+#include "luma_b200.h"
+extern "C" luma_b200_t *luma_b200_shim_handle(double *create_seconds, double *upload_seconds);   /* luma_b200/host/GridObj_ops_lbm_b200.cpp */
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -195,20 +199,55 @@ int main(int argc, char **argv)
 	else if (mode == "bench")
 	{
 		int warm = atoi(argv[2]), steps = atoi(argv[3]);
-		for (int s = 0; s < warm; ++s) Grids->LBM_multi_opt();
-		auto t0 = std::chrono::steady_clock::now();
-		for (int s = 0; s < steps; ++s) Grids->LBM_multi_opt();
-		double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		double cells = (double)Grids->N_lim * Grids->M_lim * Grids->K_lim;
 		int threads = 1;
 #if defined(_OPENMP) && defined(L_ENABLE_OPENMP)
 		threads = omp_get_max_threads();
 #endif
-		double cells = (double)Grids->N_lim * Grids->M_lim * Grids->K_lim;
+#ifdef LUMA_DROPIN
+		/* The unmodified host loop stepping on the GPU: LBM_multi_opt() once per step (src/main_lbm.cpp:441).
+		 *   first call  = case description + luma_b200_create + luma_b200_upload + step 1 (queued)
+		 *   steps       = `steps` calls, then a device sync (the calls themselves never wait)
+		 *   download    = rho,u into the GridObj arrays (what the IO points of main_lbm.cpp:449-561 need)
+		 * e2e = upload + steps + download (create -- CUDA context start-up and allocations -- is process start-up and
+		 * reported separately). */
+		auto c0 = std::chrono::steady_clock::now();
+		Grids->LBM_multi_opt();
+		double first_call = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+		double create_s = 0.0, upload_s = 0.0;
+		luma_b200_t *h = luma_b200_shim_handle(&create_s, &upload_s);
+		for (int s = 1; s < warm; ++s) Grids->LBM_multi_opt();
+		luma_b200_sync(h);
+		auto t0 = std::chrono::steady_clock::now();
+		for (int s = 0; s < steps; ++s) Grids->LBM_multi_opt();
+		double host_calls = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		luma_b200_sync(h);
+		double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		auto d0 = std::chrono::steady_clock::now();
+		Grids->LBM_multi_opt(-2);                               /* LUMA_B200_SYNC_MACRO: rho,u to the host arrays */
+		double down = std::chrono::duration<double>(std::chrono::steady_clock::now() - d0).count();
+		LumaStats st;
+		luma_b200_stats(h, &st);
+		double e2e = upload_s + secs + down;
+		printf("{\"mlups\": %.6f, \"seconds\": %.6f, \"steps\": %d, \"warmup\": %d, \"cells\": %.0f, \"threads\": %d, "
+			"\"N\": %d, \"M\": %d, \"K\": %d, \"Q\": %d, \"omega\": %.17g, \"first_call_seconds\": %.6f, \"create_seconds\": %.6f, "
+			"\"upload_seconds\": %.6f, \"download_seconds\": %.6f, \"host_seconds_in_calls\": %.6f, \"per_call_us\": %.3f, "
+			"\"seconds_e2e\": %.6f, \"mlups_e2e\": %.6f, \"graph_launches\": %lld, \"kernel_launches\": %lld}\n",
+			cells * steps / secs / 1e6, secs, steps, warm, cells, threads,
+			Grids->N_lim, Grids->M_lim, Grids->K_lim, (int)L_NUM_VELS, Grids->omega, first_call, create_s, upload_s, down,
+			host_calls, 1e6 * host_calls / steps, e2e, cells * steps / e2e / 1e6, (long long)st.graph_launches, (long long)st.kernel_launches);
+		return 0;
+#else
+		for (int s = 0; s < warm; ++s) Grids->LBM_multi_opt();
+		auto t0 = std::chrono::steady_clock::now();
+		for (int s = 0; s < steps; ++s) Grids->LBM_multi_opt();
+		double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 		printf("{\"mlups\": %.6f, \"seconds\": %.6f, \"steps\": %d, \"warmup\": %d, \"cells\": %.0f, \"threads\": %d, "
 			"\"N\": %d, \"M\": %d, \"K\": %d, \"Q\": %d, \"omega\": %.17g}\n",
 			cells * steps / secs / 1e6, secs, steps, warm, cells, threads,
 			Grids->N_lim, Grids->M_lim, Grids->K_lim, (int)L_NUM_VELS, Grids->omega);
 		return 0;
+#endif
 	}
 	fprintf(stderr, "unknown mode %s\n", mode.c_str());
 	return 1;

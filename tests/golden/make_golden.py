@@ -13,6 +13,8 @@ The digests are what pins the oracle: tests/test_oracle_pinned.py requires the C
 (oracle/luma_oracle.c) to reproduce them bit-for-bit.
 
 usage: python tests/golden/make_golden.py [case ...]
+       python tests/golden/make_golden.py --size [case ...]     # oracle.cases.SIZE_CASES: the benchmarked sizes, OpenMP build
+       python tests/golden/make_golden.py --size --check-serial c2_128   # also run the serial build and require equal digests
 """
 import hashlib
 import json
@@ -24,7 +26,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import port  # noqa: E402
-from oracle.cases import CASES  # noqa: E402
+from oracle.cases import BENCH_CASES, CASES, SIZE_CASES  # noqa: E402
 
 
 def digest(a: np.ndarray) -> str:
@@ -44,10 +46,18 @@ def probes(case, d):
     return out
 
 
-def make(name):
-    case = CASES[name]
-    res = port.run_ref_dump(name, case.steps)
-    g = {"case": name, "doc": case.doc, "reference": "cfdemons/LUMA v1.7.12 compiled (oracle/Makefile)",
+def make(name, size=False, check_serial=False):
+    case = BENCH_CASES[name] if size else CASES[name]
+    res = port.run_ref_dump(name, case.steps, omp=size)
+    if size and check_serial:
+        ser = port.run_ref_dump(name, case.steps, omp=False)
+        for tag, d in res.items():
+            for nm in ("f", "rho", "u"):
+                assert digest(d[nm]) == digest(ser[tag][nm]), ("OpenMP build differs from the serial build", name, tag, nm)
+        print("golden: %s OpenMP == serial on every snapshot" % name)
+        del ser
+    g = {"case": name, "doc": case.doc,
+         "reference": "cfdemons/LUMA v1.7.12 compiled (oracle/Makefile)" + (", OpenMP build (L_ENABLE_OPENMP)" if size else ""),
          "N": case.N, "M": case.M, "K": case.K, "Q": case.Q, "dims": case.dims, "snapshots": {}}
     init = res["init"]
     g["meta"] = init["meta"]
@@ -66,5 +76,10 @@ def make(name):
 
 
 if __name__ == "__main__":
-    for nm in (sys.argv[1:] or list(CASES)):
-        make(nm)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if "--size" in sys.argv:
+        for nm in (args or list(SIZE_CASES)):
+            make(nm, size=True, check_serial="--check-serial" in sys.argv)
+    else:
+        for nm in (args or list(CASES)):
+            make(nm)

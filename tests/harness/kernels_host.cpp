@@ -56,31 +56,29 @@ static void emu_launch(unsigned gx, unsigned gy, unsigned threads, Fn fn)
 			}
 }
 
-template <class L, int COLL>
-static void step_ft(const StepArgs &a, bool force, unsigned gx, unsigned gy, unsigned gbc, bool run_bc, bool faces)
+template <class L, int COLL, int FORCE, bool TAVG>
+static void step_kernels(const StepArgs &a, unsigned gx, unsigned gy, unsigned gbc, bool run_bc, bool faces)
 {
-	const int key = (force ? 2 : 0) | (a.tav ? 1 : 0);
 	// k_bc first, k_step second: they read fin and write disjoint sites of fout (any order gives the same result)
-	if (a.n_bc > 0 && run_bc)
-	{
-		if (key == 0) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, false, false>(a); });
-		else if (key == 1) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, false, true>(a); });
-		else if (key == 2) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, false>(a); });
-		else emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, true, true>(a); });
-	}
+	if (a.n_bc > 0 && run_bc) emu_launch(gbc, 1, 64, [&] { k_bc<L, COLL, FORCE, TAVG>(a); });
 	if (gy == 0) return;
-	if (faces)
+	if (faces) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, FORCE, TAVG>(a); });
+	else emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, FORCE, TAVG>(a); });
+}
+
+// force: 0 none, 1 + L_GRAVITY_DIRECTION (the dispatch of LUMA_DISPATCH_FT in kernels_impl.cuh)
+template <class L, int COLL>
+static void step_ft(const StepArgs &a, int force, unsigned gx, unsigned gy, unsigned gbc, bool run_bc, bool faces)
+{
+#define EMU_T(F_) do { if (a.tav) step_kernels<L, COLL, F_, true>(a, gx, gy, gbc, run_bc, faces); else step_kernels<L, COLL, F_, false>(a, gx, gy, gbc, run_bc, faces); } while (0)
+	switch (force)
 	{
-		if (key == 0) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, false, false>(a); });
-		else if (key == 1) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, false, true>(a); });
-		else if (key == 2) emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, true, false>(a); });
-		else emu_launch(gx, gy, STEP_THREADS, [&] { k_step_faces<L, COLL, true, true>(a); });
-		return;
+	case 0: EMU_T(0); break;
+	case 1: EMU_T(1); break;
+	case 2: EMU_T(2); break;
+	default: if constexpr (L::D == 3) { EMU_T(3); } break;
 	}
-	if (key == 0) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, false>(a); });
-	else if (key == 1) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, false, true>(a); });
-	else if (key == 2) emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, true, false>(a); });
-	else emu_launch(gx, gy, STEP_THREADS, [&] { k_step<L, COLL, true, true>(a); });
+#undef EMU_T
 }
 
 extern "C" {
@@ -140,7 +138,7 @@ int emu_step(const EmuCase *c, const double *fin, double *fout, const uint32_t *
 	a.rho_out = c->rho_out;
 	a.types = types; a.bcdesc = bcdesc; a.general = c->general; a.regularised = c->regularised; a.velramp_on = c->velramp_on;
 	a.tav = tav;
-	if (c->force) { a.F[c->gravity_dir] = c->rhoin * c->gravity * 1.0; a.hF[c->gravity_dir] = 0.5 * a.F[c->gravity_dir]; }
+	if (c->force) { a.Fg = c->rhoin * c->gravity * 1.0; a.hFg = 0.5 * a.Fg; }
 	a.smag_coef = 2.0 * 1.4142135623730950488016887242097 * (c->csmag * c->csmag) * c->rhoin * a.C.cs2 * a.C.cs2;
 	a.omega = c->omega;
 	a.tau = 1.0 / c->omega;
@@ -151,7 +149,8 @@ int emu_step(const EmuCase *c, const double *fin, double *fout, const uint32_t *
 	for (int side = 0; side < 2; ++side) { a.peer_f[side] = c->peer_f[side]; a.peer_stride[side] = c->peer_stride[side]; a.peer_P[side] = c->peer_P[side]; }
 
 	const unsigned gx = (a.MK + STEP_THREADS - 1) / STEP_THREADS, gy = (unsigned)(c->nplanes > 0 ? c->nplanes : 0), gbc = (unsigned)((n_bc + 63) / 64);
-	const bool force = c->force != 0, bc = c->run_bc != 0, fc = c->faces != 0;
+	const int force = c->force ? 1 + c->gravity_dir : 0;
+	const bool bc = c->run_bc != 0, fc = c->faces != 0;
 	if (c->Q == 27) step_ft<D3Q27, COLL_KBC>(a, force, gx, gy, gbc, bc, fc);
 	else if (c->Q == 19)
 	{

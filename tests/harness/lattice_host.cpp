@@ -31,25 +31,29 @@ static void make_constants(LbmConst &C, int Q)
 	for (int k = 0; k < 4; ++k) C.wden[k] = C.w[k] / C.den;
 }
 
-// one site: pulled populations fp (feed rho,u), own-site previous populations fo (KBC collides these)
-template <class L, bool FORCE>
-static void site(const double *fp, const double *fo, int kbc, double omega, const double *F3, const LbmConst &C, double *out, double *rho_out, double *u_out)
+// one site: pulled populations fp (feed rho,u), own-site previous populations fo (KBC collides these).
+// FORCE = 0 none, 1 + gravity direction; Fg = the one non-zero component of force_xyz
+template <class L, int FORCE>
+static void site(const double *fp, const double *fo, int kbc, double omega, double Fg, const LbmConst &C, double *out, double *rho_out, double *u_out)
 {
 	double f[L::Q], own[L::Q], feq[L::Q], res[L::Q], u[3], rho;
-	double F[3] = { F3[0], F3[1], F3[2] }, hF[3] = { 0.5 * F3[0], 0.5 * F3[1], 0.5 * F3[2] }, lam[4];
+	double lam[4];
 	for (int v = 0; v < L::Q; ++v) { f[v] = fp[v]; own[v] = fo[v]; }
 	for (int k = 0; k < 4; ++k) lam[k] = (1 - 0.5 * omega) * (C.w[k] / C.cs2);
-	macroscopic<L, FORCE>(f, hF, rho, u);
+	macroscopic<L, FORCE>(f, 0.5 * Fg, rho, u);
 	equilibrium_all<L>(rho, u, C, feq);
 	if (kbc)
 	{
 		const double beta_m1 = 2.0 / omega;
-		kbc_collide<L, FORCE>(u, feq, own, beta_m1, 1.0 / beta_m1, F, C, lam, res);
+		kbc_collide<L, FORCE>(u, feq, own, beta_m1, 1.0 / beta_m1, Fg, C, lam, res);
 	}
 	else
 	{
 		for (int v = 0; v < L::Q; ++v)
-			res[v] = FORCE ? f[v] + (omega * (feq[v] - f[v]) + guo_force<L>(v, u, F, C, lam)) : f[v] + omega * (feq[v] - f[v]);
+		{
+			if constexpr (FORCE != 0) res[v] = f[v] + (omega * (feq[v] - f[v]) + guo_force<L, (FORCE > 0 ? FORCE - 1 : 0)>(v, u, Fg, C, lam));
+			else res[v] = f[v] + omega * (feq[v] - f[v]);
+		}
 	}
 	for (int v = 0; v < L::Q; ++v) out[v] = res[v];
 	*rho_out = rho;
@@ -61,10 +65,20 @@ static void run(long long n, const double *fp, const double *fo, int kbc, int fo
 {
 	LbmConst C;
 	make_constants(C, L::Q);
+	int g = 0;
+	for (int d = 0; d < 3; ++d) if (F3[d] != 0.0) g = d;
+	const int code = force ? 1 + g : 0;
 	for (long long s = 0; s < n; ++s)
 	{
-		if (force) site<L, true>(fp + s * L::Q, fo + s * L::Q, kbc, omega, F3, C, out + s * L::Q, rho + s, u + s * L::D);
-		else site<L, false>(fp + s * L::Q, fo + s * L::Q, kbc, omega, F3, C, out + s * L::Q, rho + s, u + s * L::D);
+		const double *a = fp + s * L::Q, *b = fo + s * L::Q;
+		double *o = out + s * L::Q, *r = rho + s, *uu = u + s * L::D;
+		switch (code)
+		{
+		case 0: site<L, 0>(a, b, kbc, omega, 0.0, C, o, r, uu); break;
+		case 1: site<L, 1>(a, b, kbc, omega, F3[0], C, o, r, uu); break;
+		case 2: site<L, 2>(a, b, kbc, omega, F3[1], C, o, r, uu); break;
+		default: if constexpr (L::D == 3) site<L, 3>(a, b, kbc, omega, F3[2], C, o, r, uu); break;
+		}
 	}
 }
 

@@ -67,17 +67,19 @@ def main():
         ref = port.PortGrid(case)
         Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
         # both state paths and both transports, one handle (= one NCCL communicator bootstrap) each
-        modes = ("device_init", "upload+nccl")
-        if os.environ.get("LUMA_TEST_FUSED"):               # experimental fused exchange (not in the default suite until measured)
-            modes += ("device_init+fused",)
+        # three transports: peer stores by the copy kernel, NCCL send/recv, peer stores fused into the face kernels' epilogue
+        modes = ("device_init", "upload+nccl", "device_init+fused")
+        if os.environ.get("LUMA_TEST_NO_FUSED"):
+            modes = modes[:2]
         for mode in modes:
             uid = ring.broadcast_unique_id(dist, rank)      # one ncclUniqueId per communicator / handle
             g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
             if not mode.endswith("+nccl"):
                 if mode.endswith("+fused"):
                     os.environ["LUMA_B200_FUSED_HALO"] = "1"    # read by luma_b200_p2p_attach
-                ring.attach_p2p(dist, g, rank, world)       # device-initiated halo exchange; "+nccl" keeps send/recv
+                attached = ring.attach_p2p(dist, g, rank, world)       # device-initiated halo exchange; "+nccl" keeps send/recv
                 os.environ.pop("LUMA_B200_FUSED_HALO", None)
+                assert attached, "no CUDA IPC peer mapping between ring neighbours on this box"
             x0, cnt = g.x_offset, g.x_count
             ref = port.PortGrid(case)
             if mode.startswith("device_init"):
@@ -104,6 +106,7 @@ def main():
                         b = getattr(ref, nm).reshape(-1, width)[sl]
                         assert np.array_equal(a, b), "rank %d %s %s t=%d %s: %s" % (rank, name, mode, s, nm, first_diff(a.ravel(), b.ravel()))
             if case.ld_out:
+                # no barrier between the last step and forces(): a rank's share only reads its own planes
                 F = torch.tensor(g.computeLiftDrag(), dtype=torch.float64, device="cuda")
                 dist.all_reduce(F)
                 Fr = ref.force
@@ -113,7 +116,7 @@ def main():
             g.close(); ref.close()
         dist.barrier()
         if rank == 0:
-            print("mgpu ok: %s on %d GPUs (device_init with peer stores, upload with NCCL), bit-identical to the serial oracle" % (name, world), flush=True)
+            print("mgpu ok: %s on %d GPUs (%s), bit-identical to the serial oracle" % (name, world, ", ".join(modes)), flush=True)
     dist.destroy_process_group()
 
 

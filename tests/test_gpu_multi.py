@@ -21,7 +21,7 @@ def test_slabs_match_serial_oracle(world):
         names += ",cav3d_32,cav3d_tav,felid3d,kbc2d_cyl,kbc3d_chan"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29610 + world), os.path.join(HERE, "mgpu_worker.py"), names]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500)
     out = r.stdout.decode()
     assert r.returncode == 0, out[-4000:]
     assert out.count("mgpu ok") == len(names.split(",")), out[-4000:]

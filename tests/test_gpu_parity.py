@@ -259,3 +259,110 @@ def test_full_size_c2_properties():
     b.LBM_multi_opt(20)
     assert np.array_equal(b.download(capi.RHO)["rho"], ra["rho"])
     b.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# parity AT THE BENCHMARKED SIZES: golden digests of the compiled reference (OpenMP build, bit-identical to the
+# serial one) for BASELINE configs[1] at 256^3 and 128^3, and reduced-but-large configs[2] / configs[3] cases
+# (tests/golden/make_golden.py --size).  SURVEY 8(c): "C2 at 64^3-128^3 (and once at 256^3)".
+# ------------------------------------------------------------------------------------------------
+from oracle.cases import BENCH_CASES, SIZE_CASES  # noqa: E402
+
+
+def _check_against_golden_snapshots(name, g, case, gold):
+    for s in case.steps:
+        g.LBM_multi_opt(s - g.t)
+        got = g.download()
+        snap = gold["snapshots"]["t%d" % s]
+        for nm in ("f", "rho", "u"):
+            assert _digest(got[nm]) == snap[nm], (name, s, nm)
+        assert g.omega == float(snap["scalars"]["omega"])
+        if case.ld_out:
+            Fr = np.array([float(snap["scalars"][k]) for k in ("Fx", "Fy", "Fz")])
+            F = g.computeLiftDrag()
+            assert np.all(np.abs(F - Fr) <= 1e-10 * max(1.0, float(np.abs(Fr).max()))), (name, s, F, Fr)
+        del got
+
+
+@pytest.mark.parametrize("name", list(SIZE_CASES))
+@pytest.mark.parametrize("path", ["device_init", "upload_without_f", "upload"])
+def test_parity_at_size(name, path):
+    """the GPU state after the case's snapshot steps carries the sha256 digests the reference's own CPU run produced,
+    whether the state was built on the device, uploaded as rho,u,LatTyp (f = feq on the device) or uploaded in full"""
+    case = BENCH_CASES[name]
+    gold = _golden(name)
+    g = luma_b200.GridObj(defs_from_case(case))
+    if path == "device_init":
+        g.LBM_initGrid()
+    else:
+        ref = port.PortGrid(case)       # the oracle's LBM_initGrid stands in for LUMA's (no steps are run on the CPU here)
+        init = {nm: np.array(getattr(ref, nm)) for nm in ("f", "rho", "u", "lattyp")}
+        uin = [ref.uin(d) for d in range(3)]
+        ref.close()
+        assert _digest(init["f"]) == gold["snapshots"]["init"]["f"]
+        g.upload(init["f"] if path == "upload" else None, init["rho"], init["u"], init["lattyp"], *uin)
+        del init
+    got = g.download()
+    for nm in ("f", "rho", "u"):
+        assert _digest(got[nm]) == gold["snapshots"]["init"][nm], (name, "init", nm)
+    del got
+    _check_against_golden_snapshots(name, g, case, gold)
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["cav3d_32", "cyl3d", "chan3d", "tunnel2d", "cyl2d_tav", "kbc2d_cyl"])
+def test_upload_without_populations_equals_full_upload(name):
+    """f_aos = NULL (f = feq(rho,u) evaluated on the device) leaves exactly the state a full upload leaves, for the
+    L_NO_FLOW cases where the host's f is feq(rho,u) at t = 0"""
+    case = CASES[name]
+    assert case.no_flow
+    ref = port.PortGrid(case)
+    a = luma_b200.GridObj(defs_from_case(case))
+    a.upload(None, ref.rho, ref.u, ref.lattyp, ref.uin(0), ref.uin(1), ref.uin(2))
+    _assert_same(name, "init", a.download(), ref)
+    a.LBM_multi_opt(25); ref.step(25)
+    _assert_same(name, "t25", a.download(), ref, a)
+    a.close(); ref.close()
+
+
+def test_steps_are_queued_not_awaited_and_read_points_submit_them():
+    """luma_b200_step never waits; t/omega follow on the host at once; the last accepted step is held back until a read
+    point so that it is the one storing rho,u; graph batches engage although the steps arrive one call at a time"""
+    case = CASES["cav2d_c1"]
+    ref = port.PortGrid(case)
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    n = 333
+    for _ in range(n):
+        g.LBM_multi_opt()               # one step per call, LUMA's loop (src/main_lbm.cpp:441)
+    assert g.t == n                     # host-side GridObj::t is already there
+    ref.step(n)
+    _assert_same("cav2d_c1", "t%d" % n, g.download(), ref)      # read point: everything is submitted, last step stores rho,u
+    st = g.stats()
+    assert st["graph_launches"] >= (n - 1) // 16 - 1 >= 10, st
+    g.flush(); g.flush()                # idempotent
+    g.LBM_multi_opt(5); ref.step(5)
+    g.flush()                           # submit without reading
+    g.sync()
+    _assert_same("cav2d_c1", "t%d" % (n + 5), g.download(), ref)
+    # Reynolds ramp: omega on the host follows the accepted steps immediately
+    case = CASES["cav2d_reramp"]
+    ref2 = port.PortGrid(case)
+    g2 = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    for s in range(40):
+        g2.LBM_multi_opt(); ref2.step(1)
+        assert g2.omega == ref2.omega and g2.t == ref2.t
+    _assert_same("cav2d_reramp", "t40", g2.download(), ref2)
+    g.close(); g2.close(); ref.close(); ref2.close()
+
+
+def test_stats_window_covers_the_steps_between_read_points():
+    case = CASES["cav3d_64"]
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    g.LBM_multi_opt(50)
+    st = g.stats()
+    assert st["steps"] == 50 and st["ms_last_call"] > 0
+    assert abs(st["ms_per_step"] * 50 - st["ms_last_call"]) < 1e-9 * max(1.0, st["ms_last_call"])
+    g.LBM_multi_opt(20)
+    st2 = g.stats()
+    assert st2["steps"] == 70 and abs(st2["ms_per_step"] * 20 - st2["ms_last_call"]) < 1e-9 * max(1.0, st2["ms_last_call"])
+    g.close()

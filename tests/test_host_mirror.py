@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(names) >= 18
     for nm in names:
         assert hasattr(L, nm), "symbol %s declared in include/luma_b200.h is not exported" % nm
-    assert L.luma_b200_abi_version() == 3
+    assert L.luma_b200_abi_version() == 4
 
 
 def test_struct_layout_matches_header():

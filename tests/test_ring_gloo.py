@@ -101,3 +101,60 @@ def test_plan_is_empty_for_a_single_rank_and_symmetric_otherwise():
                 s = [m["pop"] for m in plans[r] if m["is_send"] and m["peer"] == peer]
                 rcv = [m["pop"] for m in plans[peer] if (not m["is_send"]) and m["peer"] == r]
                 assert s == rcv, (world, r, peer)
+
+
+class _FakeGrid:
+    """stands in for a GridObj in the transport negotiation (no GPU here): export / attach succeed or fail on demand"""
+    def __init__(self, export_ok, attach_ok):
+        self.export_ok, self.attach_ok, self.attached = export_ok, attach_ok, False
+
+    def p2p_export(self):
+        if not self.export_ok:
+            raise RuntimeError("no IPC on this device")
+        return bytes(256)
+
+    def p2p_attach(self, left, right):
+        assert len(left) == 256 and len(right) == 256
+        if not self.attach_ok:
+            raise RuntimeError("cudaIpcOpenMemHandle failed")
+        self.attached = True
+
+
+def _attach_worker(rank, world, port_no, scenario, q):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port_no)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        export_ok = not (scenario == "export_fails_on_1" and rank == 1)
+        attach_ok = not (scenario == "attach_fails_on_1" and rank == 1) and scenario != "attach_fails_everywhere"
+        g = _FakeGrid(export_ok, attach_ok)
+        try:
+            res = ring.attach_p2p(dist, g, rank, world)
+        except RuntimeError as ex:
+            res = "raised"
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, res, g.attached))
+    except Exception:   # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc(), False))
+
+
+@pytest.mark.parametrize("scenario,expect", [("all_ok", True), ("export_fails_on_1", False), ("attach_fails_everywhere", False),
+                                             ("attach_fails_on_1", "raised")])
+def test_transport_choice_is_collective(scenario, expect):
+    """ring.attach_p2p: every rank ends with the same answer -- peer stores everywhere, NCCL everywhere (and then NO rank has
+    attached), or an exception everywhere when the mappings opened on some ranks only"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_attach_worker, args=(r, world, port_no, scenario, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [expect] * world, res
+    if expect is False:
+        assert not any(r[2] for r in res) or scenario == "attach_fails_everywhere", res
