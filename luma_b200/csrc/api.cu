@@ -138,6 +138,7 @@ struct luma_b200
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
 	int geometry_epoch = 0;         // bumped by upload / init_synthetic
+	bool use_tma = false;           // LUMA_B200_TMA=1 at create: the shared-memory-staged variant of k_step (profiles/r02_variants.txt)
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
 	size_t prof_used = 0;
@@ -327,6 +328,12 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	h->MK = (long long)p->M * p->K;
 	h->cells = (long long)h->P * h->MK;
 	h->stride = (h->cells + 15) / 16 * 16;
+	{
+		// tuning knob (profiles/r02_variants.txt): extra elements between the population arrays, a multiple of 16, so that
+		// the Q read streams and Q write streams of the step do not sit at power-of-two distances from each other
+		const char *pv = getenv("LUMA_B200_STRIDE_PAD");
+		if (pv && *pv && atoll(pv) > 0) h->stride += (atoll(pv) + 15) / 16 * 16;
+	}
 	h->omega = p->omega;
 	h->t = p->t;
 	memset(&h->st, 0, sizeof(h->st));
@@ -342,6 +349,10 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 		h->graph_steps = gsteps & ~1;
 	}
 	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
+	{
+		const char *tv = getenv("LUMA_B200_TMA");
+		h->use_tma = tv && *tv && atoi(tv) != 0;
+	}
 
 	int ndev = 0;
 	CK(cudaGetDeviceCount(&ndev));
@@ -1022,6 +1033,7 @@ static void fill_step_args(luma_b200_t *h, StepArgs &a)
 	a.cw = h->cw; a.rho = h->rho; a.u = h->u; a.stride = h->stride;
 	a.P = h->P; a.M = p.M; a.K = p.K; a.MK = (unsigned)h->MK;
 	a.wrap_x = h->ghost ? 0 : 1;
+	a.use_tma = h->use_tma ? 1 : 0;
 	a.C = h->C;
 	for (int v = 0; v < h->Q; ++v)
 	{

@@ -20,6 +20,7 @@ struct StepArgs
 	int wrap_x;               // 1: periodic wrap inside the array (single rank); 0: ghost planes 0 and P-1
 	int p0, pstep;            // plane handled by blockIdx.y: p0 + blockIdx.y * pstep
 	int write_macro;          // store rho,u of fluid sites (last step of a call)
+	int use_tma;              // k_step_tma (loads staged through shared memory by bulk copies) instead of k_step
 	double omega;
 	double tau;               // 1.0 / omega
 	double smag_coef;         // 2.0*L_SQRT2*SQ(L_CSMAG)*L_RHOIN*SQ(cs)*SQ(cs)          optimised.cpp:752

@@ -339,6 +339,108 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step_faces(const StepArgs a)
 	step_site<L, COLL, FORCE, TAVG, true>(a);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variant of k_step whose loads are STAGED THROUGH SHARED MEMORY BY THE TMA ENGINE (LUMA_B200_TMA=1; measured against
+// the per-thread-load kernel in profiles/r02_variants.txt).  One CTA = one run of STEP_THREADS consecutive sites of an
+// x-plane.  In the SoA layout the values those sites pull for population v are one CONTIGUOUS run of the lattice, shifted
+// by c_v -- so thread 0 issues Q one-dimensional bulk copies (cp.async.bulk.shared.global, SASS UBLKCP) of ~1 KB each,
+// all completing on one mbarrier, and every thread then reads its Q values from shared memory (conflict-free).  Bulk
+// copies need 16-byte aligned addresses and sizes: a run shifted by an odd number of elements (c_z = +-1) is copied from
+// one element earlier, two elements longer.  What TMA cannot express stays per thread: sites with a bounce-back link, on
+// the first/last row or column (periodic wrap), or in a tile whose shifted runs leave the array (first/last planes) take
+// the ordinary pull_populations path; stores are per thread as well, because a tile also holds sites this kernel must
+// not write (solid sites keep their state, boundary sites belong to k_bc).
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#endif
+
+template <class L, int COLL, int FORCE, bool TAVG>
+__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_step_tma(const StepArgs a)
+{
+#ifdef __CUDACC__
+	constexpr int T = STEP_THREADS;
+	constexpr int ROW = T + 2;
+	__shared__ __align__(16) double tile[L::Q][ROW];
+	__shared__ __align__(8) unsigned long long bar;
+	__shared__ int staged;
+	const unsigned r0 = blockIdx.x * T;
+	const int p = a.p0 + (int)blockIdx.y * a.pstep;
+	const long long id0 = (long long)p * a.MK + r0;
+	const int n = (int)((a.MK - r0) < (unsigned)T ? (a.MK - r0) : (unsigned)T);
+	const long long cells = (long long)a.P * a.MK;
+	if (threadIdx.x == 0)
+	{
+		// every shifted run must lie inside the lattice array, else the whole tile takes the per-thread path
+		bool ok = !(a.wrap_x && (p == 0 || p == a.P - 1));
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v)
+		{
+			const long long start = id0 - ((long long)L::c(v, 0) * a.MK + (long long)L::c(v, 1) * a.K + L::c(v, 2));
+			const long long odd = start & 1;
+			if (start - odd < 0 || start - odd + ((n + odd + 1) & ~1LL) > cells) ok = false;
+		}
+		staged = ok ? 1 : 0;
+		const uint32_t b = smem_u32(&bar);
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		if (ok)
+		{
+			uint32_t total = 0;
+#pragma unroll
+			for (int v = 0; v < L::Q; ++v)
+			{
+				const long long start = id0 - ((long long)L::c(v, 0) * a.MK + (long long)L::c(v, 1) * a.K + L::c(v, 2));
+				total += (uint32_t)(((n + (start & 1) + 1) & ~1LL) * 8);
+			}
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(total) : "memory");
+#pragma unroll
+			for (int v = 0; v < L::Q; ++v)
+			{
+				const long long start = id0 - ((long long)L::c(v, 0) * a.MK + (long long)L::c(v, 1) * a.K + L::c(v, 2));
+				const long long odd = start & 1;
+				const uint32_t bytes = (uint32_t)(((n + odd + 1) & ~1LL) * 8);
+				const double *src = a.fin + (long long)v * a.stride + (start - odd);
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					:: "r"(smem_u32(&tile[v][0])), "l"(src), "r"(bytes), "r"(b) : "memory");
+			}
+		}
+	}
+	__syncthreads();
+	const unsigned r = r0 + threadIdx.x;
+	const bool live = (int)threadIdx.x < n;
+	const long long id = id0 + threadIdx.x;
+	const uint32_t w = live ? __ldg(a.cw + id) : 0u;
+	if (staged)
+	{
+		const uint32_t b = smem_u32(&bar);
+		asm volatile("{\n .reg .pred q;\n LUMA_TMA_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 q, [%0], 0;\n @q bra LUMA_TMA_DONE;\n bra LUMA_TMA_WAIT;\n LUMA_TMA_DONE:\n}"
+			:: "r"(b) : "memory");
+	}
+	if (!live || cw_class<L>(w) != CLS_FLUID) return;
+
+	double f[L::Q], feq[L::Q], u[3], rho;
+	if (staged && (w & (CW<L>::LINKS | CW<L>::EDGE)) == 0)
+	{
+		// parity of the shifted start == parity of c_z when M*K and K are even (checked by the launcher)
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v) f[v] = tile[v][threadIdx.x + ((L::c(v, 2) != 0) ? 1 : 0)];
+	}
+	else pull_populations<L>(a, p, r, id, w, f);
+	macroscopic<L, FORCE>(f, a.hFg, rho, u);
+	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
+	equilibrium_all<L>(rho, u, a.C, feq);
+	collide<L, COLL, FORCE>(a, id, u, feq, f);
+	store_populations<L>(a, id, f);
+	if (a.write_macro)
+	{
+		a.rho[id] = rho;
+#pragma unroll
+		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
+	}
+#endif
+}
+
 // new-time rho,u of an extrapolation neighbour: GridObj::_LBM_updateAndExtrapolate +
 // _LBM_updateInteriorLatticeSite (optimised.cpp:1353-1434).  A fluid neighbour is streamed and
 // "macro'd" from the old lattice here; any other type keeps its stored values (its macro is a no-op).
@@ -636,7 +738,9 @@ template <class L> void launch_step(const StepArgs &a, int coll, int force, int 
 {
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
-	LUMA_DISPATCH(k_step, grid, STEP_THREADS);
+	// the TMA-staged variant needs even M*K and K (16-byte aligned bulk copies) and the start of a tile on an even element
+	if (a.use_tma && (a.MK & 1u) == 0 && (a.K & 1) == 0) LUMA_DISPATCH(k_step_tma, grid, STEP_THREADS);
+	else LUMA_DISPATCH(k_step, grid, STEP_THREADS);
 	if (launches) ++*launches;
 }
 

@@ -9,6 +9,14 @@
  * point is a no-op returning MPI_SUCCESS; they exist only to satisfy the
  * compiler for translation units such as src/MpiManager.cpp.
  */
+/* Syntax check of the MPI branch of luma_b200/host/GridObj_ops_lbm_b200.cpp (tests/test_host_mirror.py): in a real LUMA
+ * build L_BUILD_FOR_MPI comes from inc/definitions.h, which inc/stdafx.h includes at :203 -- AFTER errorfcn (:135-149), so
+ * that function's MPI lines are never compiled.  The oracle's case header is force-included ahead of everything (and pulls
+ * this file in once, oracle/cases/luma_case_tail.h), so the macro is raised on the SECOND inclusion instead: that is
+ * inc/stdafx.h:205, right behind definitions.h / GridManager.h and in front of inc/MpiManager.h. */
+#if defined(LUMA_SHIM_MPI_SYNTAX) && defined(LUMA_B200_ORACLE_MPI_SHIM_H) && !defined(L_BUILD_FOR_MPI)
+#define L_BUILD_FOR_MPI
+#endif
 #ifndef LUMA_B200_ORACLE_MPI_SHIM_H
 #define LUMA_B200_ORACLE_MPI_SHIM_H
 
@@ -30,6 +38,7 @@ enum {
 };
 enum { MPI_DOUBLE = 1, MPI_INT, MPI_LONG, MPI_CHAR, MPI_UNSIGNED, MPI_C_BOOL };
 enum { MPI_SUM = 1, MPI_MAX, MPI_MIN };
+enum { MPI_COMM_TYPE_SHARED = 1 };
 
 #define MPI_STATUS_IGNORE   ((MPI_Status *)0)
 #define MPI_STATUSES_IGNORE ((MPI_Status *)0)
@@ -51,6 +60,7 @@ LUMA_ORACLE_MPI_FN(MPI_Recv)          LUMA_ORACLE_MPI_FN(MPI_Bsend)
 LUMA_ORACLE_MPI_FN(MPI_Sendrecv_replace)
 LUMA_ORACLE_MPI_FN(MPI_Wait)          LUMA_ORACLE_MPI_FN(MPI_Waitall)
 LUMA_ORACLE_MPI_FN(MPI_Comm_split)    LUMA_ORACLE_MPI_FN(MPI_Comm_free)
+LUMA_ORACLE_MPI_FN(MPI_Comm_split_type)
 LUMA_ORACLE_MPI_FN(MPI_Gather)        LUMA_ORACLE_MPI_FN(MPI_Gatherv)
 LUMA_ORACLE_MPI_FN(MPI_Scatter)       LUMA_ORACLE_MPI_FN(MPI_Scatterv)
 LUMA_ORACLE_MPI_FN(MPI_Alltoall)      LUMA_ORACLE_MPI_FN(MPI_Alltoallv)

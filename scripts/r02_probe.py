@@ -1,0 +1,58 @@
+"""Development probe (not the bench contract): device time of the step for (case x size x knob) combinations, to see what
+the kernel's bandwidth depends on.  usage: python scripts/r02_probe.py [quick]   (one B200)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import luma_b200
+E = luma_b200
+
+
+def defs(case, res):
+    if case == "cavity":
+        return E.Definitions(L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=1000.0, L_UX0=1.0, L_WALL_TOP=E.eVelocity,
+                             L_REGULARISED_BOUNDARIES=True, L_NO_FLOW=True)
+    if case == "box":        # closed box, all walls solid, no lid: no list kernel at all
+        return E.Definitions(L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=1000.0, L_NO_FLOW=True)
+    force = case == "channel_f"
+    smag = case == "channel_s"
+    return E.Definitions(L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=None, L_NU=1.0 / res, L_NO_FLOW=True,
+                         L_WALL_LEFT=E.eFluid, L_WALL_RIGHT=E.eFluid, L_WALL_FRONT=E.eFluid, L_WALL_BACK=E.eFluid,
+                         L_WALL_THICKNESS_CELLS=(0, 0, 1, 1, 0, 0), L_USE_BGKSMAG=smag,
+                         L_GRAVITY_ON=force, L_GRAVITY_FORCE=0.0158 if force else 0.0, L_GRAVITY_DIRECTION=0)
+
+
+def run(case, res, steps, env=None):
+    for k in ("LUMA_B200_TMA", "LUMA_B200_STRIDE_PAD"):
+        os.environ.pop(k, None)
+    os.environ.update(env or {})
+    g = E.GridObj(defs(case, res)).LBM_initGrid()
+    g.LBM_multi_opt(10); g.sync()
+    best = None
+    for _ in range(2):
+        g.LBM_multi_opt(steps)
+        st = g.stats()
+        if best is None or st["ms_per_step"] < best:
+            best = st["ms_per_step"]
+    g.set_profiling(True)
+    g.LBM_multi_opt(20)
+    sp = g.stats()
+    g.set_profiling(False)
+    kms = sp["step_kernel_ms"] / max(1, sp["step_kernel_launches"])
+    cells = res ** 3
+    print("%-10s %4d^3 %-28s step %.4f ms  %6.0f MLUPS  %5.0f GB/s | k_step alone %.4f ms %5.0f GB/s" % (
+        case, res, ",".join("%s=%s" % (k.replace("LUMA_B200_", ""), v) for k, v in (env or {}).items()) or "-",
+        best, cells / best / 1e3, cells * 304 / best / 1e6, kms, cells * 304 / kms / 1e6), flush=True)
+    g.close()
+
+
+if __name__ == "__main__":
+    quick = len(sys.argv) > 1
+    for res in (256, 384, 512):
+        st = {256: 300, 384: 100, 512: 40}[res]
+        for case in ("cavity", "box", "channel", "channel_f", "channel_s"):
+            run(case, res, st)
+            run(case, res, st, {"LUMA_B200_TMA": "1"})
+        if quick:
+            continue
+        for pad in (16, 272, 4112, 65552):
+            run("cavity", res, st, {"LUMA_B200_STRIDE_PAD": str(pad)})
+        run("channel_f", res, st, {"LUMA_B200_STRIDE_PAD": "4112"})

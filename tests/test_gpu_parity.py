@@ -277,8 +277,10 @@ def _check_against_golden_snapshots(name, g, case, gold):
         for nm in ("f", "rho", "u"):
             assert _digest(got[nm]) == snap[nm], (name, s, nm)
         assert g.omega == float(snap["scalars"]["omega"])
-        if case.ld_out:
-            Fr = np.array([float(snap["scalars"][k]) for k in ("Fx", "Fy", "Fz")])
+        if case.ld_out and "scalars_serial" in snap:
+            # momentum-exchange force: only the SERIAL reference build gives one (the OpenMP build accumulates it in a data
+            # race, see note_scalars in the golden file); cross-site sum -> tolerance, order documented in DESIGN.md
+            Fr = np.array([float(snap["scalars_serial"][k]) for k in ("Fx", "Fy", "Fz")])
             F = g.computeLiftDrag()
             assert np.all(np.abs(F - Fr) <= 1e-10 * max(1.0, float(np.abs(Fr).max()))), (name, s, F, Fr)
         del got

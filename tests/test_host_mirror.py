@@ -119,3 +119,21 @@ def test_definitions_derive_the_reference_scalars(name):
     for s in (0, 1, 7, 100):
         assert d.velocity_ramp_coefficient(s * d.dt) == g.velocity_ramp(s * d.dt)
     g.close()
+
+
+def test_mpi_branch_of_the_dropin_shim_compiles():
+    """The L_BUILD_FOR_MPI branch of luma_b200/host/GridObj_ops_lbm_b200.cpp (one rank per GPU: MPI_Bcast of the NCCL id,
+    node-local device choice, collective choice of the halo transport) compiled against the unmodified LUMA headers and the
+    serial <mpi.h> stand-in.  oracle/shim/mpi.h explains how L_BUILD_FOR_MPI is raised at the point where a real LUMA build
+    sees it (inc/stdafx.h:203-206).  Needs the reference sources; the image has no MPI to link and run it."""
+    import subprocess
+    if not os.path.exists("/root/reference/LUMA/inc/stdafx.h"):
+        pytest.skip("reference sources not present")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O0", "-std=c++0x", "-w", "-include", "limits", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I/root/reference",
+           "-include", os.path.join(ROOT, "oracle", "cases", "chan3d.h"), "-I" + os.path.join(ROOT, "include"),
+           "-DLUMA_SHIM_MPI_SYNTAX", "-c", os.path.join(ROOT, "luma_b200", "host", "GridObj_ops_lbm_b200.cpp"), "-o", "/dev/null"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()[-3000:]
+    pre = subprocess.run(cmd[:-4] + ["-E", cmd[-3]], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+    assert "MPI_Allgather" in pre and "MPI_Comm_split_type" in pre and "luma_b200_p2p_attach" in pre      # the branch was really compiled
