@@ -315,8 +315,7 @@ def parity_check(rank, world, local, dist, halo_mode, ring):
         if world > 1:
             transport = "nccl"
             if halo_mode in ("p2p", "fused"):
-                if halo_mode == "fused":
-                    os.environ["LUMA_B200_FUSED_HALO"] = "1"
+                os.environ["LUMA_B200_FUSED_HALO"] = "1" if halo_mode == "fused" else "0"
                 if ring.attach_p2p(dist, g, rank, world):
                     transport = halo_mode
                 os.environ.pop("LUMA_B200_FUSED_HALO", None)
@@ -354,15 +353,13 @@ def make_grid(defs, rank, world, local, dist, halo_mode, ring):
         nface = {9: 3, 19: 5, 27: 9}[Q]
         halo = "NCCL send/recv of the %d outgoing populations per face" % nface
         if halo_mode in ("p2p", "fused"):
-            if halo_mode == "fused":
-                os.environ["LUMA_B200_FUSED_HALO"] = "1"       # read by luma_b200_p2p_attach
+            os.environ["LUMA_B200_FUSED_HALO"] = "1" if halo_mode == "fused" else "0"       # read by luma_b200_p2p_attach
             # peer stores need CUDA IPC peer mappings between ring neighbours; ring.attach_p2p agrees on the outcome across
             # the ranks, and where a box cannot provide the mappings every rank uses the NCCL exchange together
             if ring.attach_p2p(dist, g, rank, world):
                 halo = ("device-initiated: the %d outgoing populations per face stored into the neighbour's ghost plane over "
                         "NVLink (CUDA IPC), arrival flags" % nface)
-                if halo_mode == "fused":
-                    halo += "; stores fused into the face kernels' epilogue"
+                halo += ("; stores fused into the face kernels' epilogue" if halo_mode == "fused" else "; separate copy kernel")
             else:
                 halo += " (peer mapping unavailable on this box)"
             os.environ.pop("LUMA_B200_FUSED_HALO", None)
@@ -615,9 +612,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5", "k27"], default=DEFAULT_WORKLOAD)
-    ap.add_argument("--halo", choices=["p2p", "nccl", "fused"], default="p2p",
-                    help="multi-GPU halo exchange: peer stores by a copy kernel (default), NCCL send/recv, or (experimental) peer stores "
-                         "fused into the face kernels' epilogue")
+    ap.add_argument("--halo", choices=["p2p", "nccl", "fused"], default="fused",
+                    help="multi-GPU halo exchange: peer stores fused into the face kernels' epilogue (default), peer stores by a separate "
+                         "copy kernel (p2p), or NCCL send/recv")
     ap.add_argument("--res", type=int, default=None, help="cavity edge per GPU for c2/c5 (scaling studies; not the named config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -166,9 +166,10 @@ int  luma_b200_comm_init(luma_b200_t *h, const void *unique_id_128);
  * populations straight into the neighbour GPU's ghost planes over NVLink and signals arrival with a flag -- no
  * communication-library call per step.  Needs peer access between neighbouring GPUs (NVSwitch: always); without
  * attach the NCCL send/recv path below runs.  Results are identical either way.
- * Experimental: with LUMA_B200_FUSED_HALO=1 in the environment at attach time the stores move into the epilogue of the
- * face-plane kernels (no copy kernel; one flag-publish launch); logic checked on the CPU against the oracle, not yet
- * measured on hardware, hence off by default. */
+ * The stores are part of the epilogue of the face-plane kernels (compute and transfer are one kernel; a one-thread launch
+ * publishes the arrival flags); LUMA_B200_FUSED_HALO=0 in the environment at attach time selects the older form, a separate
+ * copy kernel after the face kernels.  All three transports are parity-tested (tests/test_gpu_multi.py) and measured
+ * (profiles/r02_halo_transports_n2.txt). */
 #define LUMA_B200_P2P_BLOB_BYTES 256
 int  luma_b200_p2p_export(luma_b200_t *h, void *blob_256);
 int  luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob_256, const void *right_blob_256);
@@ -238,6 +239,14 @@ int  luma_b200_download_wait(luma_b200_t *h);
  *      host that kept them across a restart hand them back.  NULL pointers are skipped. ---- */
 int  luma_b200_download_timeav(luma_b200_t *h, int32_t halo, double *rho_timeav, double *ui_timeav, double *uiuj_timeav);
 int  luma_b200_upload_timeav(luma_b200_t *h, int32_t halo, const double *rho_timeav, const double *ui_timeav, const double *uiuj_timeav);
+
+/* ---- binary restart: t, omega, nu, rho, u, f and -- for handles created with time_averaged -- the three
+ *      averages of this rank's owned planes, raw little-endian doubles in the reference's array layouts behind a 64-byte
+ *      header; the content of GridObj::io_restart (src/GridObj_ops_io.cpp:406-640), which spends 17 decimal digits of ASCII
+ *      per value.  One file per rank.  restart_read needs the geometry first (luma_b200_upload of the freshly initialised
+ *      grid with f_aos = NULL, or luma_b200_init_synthetic) and replaces t and the fields; the run continues bit-identically. ---- */
+int  luma_b200_restart_write(luma_b200_t *h, const char *path);
+int  luma_b200_restart_read(luma_b200_t *h, const char *path);
 
 /* ---- scalars the host object keeps in step with the device (GridObj::t, ::omega, ::nu) ---- */
 int  luma_b200_get_time(luma_b200_t *h, int32_t *t, double *omega, double *nu);

@@ -51,13 +51,17 @@ def is_current() -> bool:
 
 
 def build_variant(tag: str, defines) -> str:
-    """Development aid: an extra library built with -D tuning knobs (kernels.cu), e.g.
-    build_variant("t128", ["-DLUMA_STEP_THREADS=128"]) -> luma_b200/libluma_b200_t128.so."""
+    """Development aid: an extra library whose D3Q19 kernels are built with -D tuning knobs (kernels_impl.cuh), e.g.
+    build_variant("t256b3", ["-DLUMA_STEP_THREADS=256", "-DLUMA_MIN_BLOCKS=3"]) -> luma_b200/libluma_b200_t256b3.so
+    (select it with LUMA_B200_LIB).  The other translation units are the default build's objects."""
+    build()
     nvcc = _nvcc()
+    bdir = os.path.join(HERE, "build")
     out = os.path.join(HERE, "libluma_b200_%s.so" % tag)
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.run([nvcc] + NVCC_FLAGS + list(defines) + ["-I", "/usr/include", "-shared", "-o", out] + srcs + ["-ldl"],
-                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    obj = os.path.join(bdir, "kernels_d3q19_%s.o" % tag)
+    subprocess.run([nvcc] + NVCC_FLAGS + list(defines) + ["-I", "/usr/include", "-c", os.path.join(CSRC, "kernels_d3q19.cu"), "-o", obj], check=True)
+    objs = [os.path.join(bdir, s.replace(".cu", ".o")) for s in SOURCES if s != "kernels_d3q19.cu"] + [obj]
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl"], check=True)
     return out
 
 

@@ -113,6 +113,8 @@ def load(build_if_missing: bool = True):
     L.luma_b200_init_synthetic.argtypes = [H, C.POINTER(LumaSyntheticCase)]
     L.luma_b200_step.argtypes = [H, C.c_int32]
     L.luma_b200_flush.argtypes = [H]
+    L.luma_b200_restart_write.argtypes = [H, C.c_char_p]
+    L.luma_b200_restart_read.argtypes = [H, C.c_char_p]
     L.luma_b200_download.argtypes = [H, C.c_int32, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
     L.luma_b200_download_lattyp.argtypes = [H, C.c_int32, C.c_void_p]
     L.luma_b200_download_async.argtypes = [H, C.c_int32, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -126,7 +128,7 @@ def load(build_if_missing: bool = True):
     L.luma_b200_set_profiling.argtypes = [H, C.c_int32]
     L.luma_b200_halo_plan.argtypes = [C.POINTER(LumaCaseParams), C.POINTER(LumaHaloMsg), C.c_int32, _ip]
     L.luma_b200_selftest_div_const.argtypes = [C.c_int32, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
-    for nm in ("flush", "create", "slab", "comm_unique_id", "comm_init", "p2p_export", "p2p_attach", "upload", "init_synthetic", "step", "download",
+    for nm in ("restart_write", "restart_read", "flush", "create", "slab", "comm_unique_id", "comm_init", "p2p_export", "p2p_attach", "upload", "init_synthetic", "step", "download",
                "download_lattyp", "download_async", "download_wait", "download_timeav", "upload_timeav", "get_time", "forces", "stats", "sync", "set_profiling", "selftest_div_const", "halo_plan"):
         getattr(L, "luma_b200_" + nm).restype = C.c_int
     if L.luma_b200_abi_version() != 4:

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <utility>
 #include <vector>
@@ -133,12 +134,13 @@ struct luma_b200
 	volatile int *halo_timeout_host = nullptr;   // the same word as the host reads it: polled without any stream traffic
 	PeerMap peer[2];                       // 0 = left (rank-1), 1 = right (rank+1); peer[1] aliases peer[0] when nranks == 2
 	bool p2p = false;
-	bool fused = false;                    // LUMA_B200_FUSED_HALO=1 at attach time: the face kernels store into the neighbours' ghost planes themselves
+	bool fused = false;                    // the face kernels store into the neighbours' ghost planes themselves (default with peer stores; LUMA_B200_FUSED_HALO=0: copy kernel)
 	unsigned long long xchg = 0;           // exchanges published so far
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
 	int geometry_epoch = 0;         // bumped by upload / init_synthetic
-	bool use_tma = false;           // LUMA_B200_TMA=1 at create: the shared-memory-staged variant of k_step (profiles/r02_variants.txt)
+	bool fill_holes = false;        // LUMA_B200_FILL=1: copy never-updated sites through where they share a 64-byte block with updated ones
+	int use_tma = 0;                // LUMA_B200_TMA=1 / LUMA_B200_V2=1 at create: measured variants of k_step (profiles/r02_variants.txt)
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
 	size_t prof_used = 0;
@@ -350,8 +352,10 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 	}
 	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 	{
-		const char *tv = getenv("LUMA_B200_TMA");
-		h->use_tma = tv && *tv && atoi(tv) != 0;
+		const char *tv = getenv("LUMA_B200_TMA"), *v2 = getenv("LUMA_B200_V2");
+		h->use_tma = (tv && *tv && atoi(tv) != 0) ? 1 : ((v2 && *v2 && atoi(v2) != 0) ? 2 : 0);
+		const char *fv = getenv("LUMA_B200_FILL");
+		h->fill_holes = fv && *fv && atoi(fv) != 0;
 	}
 
 	int ndev = 0;
@@ -502,9 +506,10 @@ int luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob, const void *righ
 	}
 	h->p2p = true;
 	{
-		// experimental (not yet measured on hardware): fold the peer stores into the face kernels' epilogue
+		// the peer stores are part of the face kernels' epilogue (default: measured best at every slab size,
+		// profiles/r02_halo_transports_n2.txt); LUMA_B200_FUSED_HALO=0 keeps the separate copy kernel k_halo_push
 		const char *fv = getenv("LUMA_B200_FUSED_HALO");
-		h->fused = fv && *fv && atoi(fv) != 0;
+		h->fused = !(fv && *fv && atoi(fv) == 0);
 	}
 	return LUMA_B200_OK;
 }
@@ -843,6 +848,11 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	CK(cudaStreamSynchronize(h->s_comm));
 	CK(cudaStreamSynchronize(h->s_main));
 	h->stream_joined = true;
+	// LUMA_B200_TRACE=1: wall time of the phases of this call on stderr (development aid)
+	const bool trace = getenv("LUMA_B200_TRACE") != nullptr;
+	auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_begin = now();
+	double t_copies = 0.0, t_desc = 0.0, t_geom = 0.0;
 	const long long owned = (long long)p.x_count * h->MK;
 	const long long host_off = (long long)halo * h->MK;       // first owned site in the host arrays
 	const long long dev_off = (long long)h->ghost * h->MK;    // first owned site on the device
@@ -892,6 +902,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	if (uz_in) memcpy(&uin[2 * (size_t)p.M], uz_in, sizeof(double) * p.M);
 	CK(cudaMemcpyAsync(h->uin, uin.data(), uin.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
 
+	if (trace) { cudaStreamSynchronize(h->s_main); t_copies = now(); }
 	// wall descriptors of the boundary sites: sparse on the host, scattered into the dense device array
 	std::vector<long long> dsite;
 	std::vector<uint32_t> dval;
@@ -933,6 +944,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	}
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(h->s_main));
+	t_desc = now();
 
 	rc = finalize_geometry(h, [&](long long id, int, int, int) -> uint32_t
 	{
@@ -940,6 +952,7 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 		return (it != dsite.end() && *it == id) ? dval[(size_t)(it - dsite.begin())] : 0u;
 	});
 	if (rc) return rc;
+	t_geom = now();
 	if (h->ghost)
 	{
 		rc = exchange_populations(h, h->f[h->cur], h->s_main);
@@ -953,6 +966,9 @@ int luma_b200_upload(luma_b200_t *h, int32_t halo, const double *f_aos, const do
 	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 	h->have_state = true; h->stepped = false;
 	++h->geometry_epoch;
+	if (trace)
+		fprintf(stderr, "luma_b200_upload: %.1f ms = host->device copies + layout kernels %.1f, wall descriptors %.1f, geometry (eType scan, lists, cell words) %.1f, "
+			"ghost exchange + second lattice %.1f\n", now() - t_begin, t_copies - t_begin, t_desc - t_copies, t_geom - t_desc, now() - t_geom);
 	return halo_health(h);
 }
 
@@ -1033,7 +1049,8 @@ static void fill_step_args(luma_b200_t *h, StepArgs &a)
 	a.cw = h->cw; a.rho = h->rho; a.u = h->u; a.stride = h->stride;
 	a.P = h->P; a.M = p.M; a.K = p.K; a.MK = (unsigned)h->MK;
 	a.wrap_x = h->ghost ? 0 : 1;
-	a.use_tma = h->use_tma ? 1 : 0;
+	a.use_tma = h->use_tma;
+	a.fill_holes = h->fill_holes ? 1 : 0;
 	a.C = h->C;
 	for (int v = 0; v < h->Q; ++v)
 	{
@@ -1526,6 +1543,129 @@ int luma_b200_upload_timeav(luma_b200_t *h, int32_t halo, const double *rho_time
 	if (!h) return LUMA_B200_EINVAL;
 	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "upload_timeav before upload/init_synthetic");
 	return transfer_timeav(h, halo, const_cast<double *>(rho_timeav), const_cast<double *>(ui_timeav), const_cast<double *>(uiuj_timeav), false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Binary restart.  GridObj::io_restart (src/GridObj_ops_io.cpp:406-640) writes / reads the level-0 state as
+// ASCII, one line per site (indices, Q populations, rho, u, time averages); this is the same content -- t, f, rho, u and,
+// when the handle has them, rho_timeav / ui_timeav / uiuj_timeav of this rank's owned planes, in the reference's array
+// layouts -- as raw little-endian doubles behind a small header, streamed through the staging buffer in chunks.
+// ------------------------------------------------------------------------------------------------
+struct RestartHeader
+{
+	char magic[8];            // "LUMAB2R1"
+	int32_t dims, num_vels, N, M, K, x_offset, x_count, t;
+	int32_t has_timeav, reserved;
+	double omega, nu;
+};
+
+static int restart_stream(luma_b200_t *h, FILE *fh, bool write, double *soa_or_field, int ncomp, bool soa)
+{
+	// one field of `ncomp` doubles per site (ncomp = 1: plain copy; > 1: device SoA <-> file AoS), owned planes only
+	const long long owned = (long long)h->p.x_count * h->MK, dev_off = (long long)h->ghost * h->MK;
+	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(64u << 20) / (ncomp * 8)));
+	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
+	if (rc) return rc;
+	std::vector<double> host((size_t)chunk * ncomp);
+	for (long long c0 = 0; c0 < owned; c0 += chunk)
+	{
+		const long long n = std::min(chunk, owned - c0);
+		const size_t bytes = (size_t)n * ncomp * sizeof(double);
+		if (write)
+		{
+			if (!soa) CK(cudaMemcpyAsync(host.data(), soa_or_field + dev_off + c0, bytes, cudaMemcpyDeviceToHost, h->s_main));
+			else
+			{
+				if (ncomp == h->Q) LAT(h->Q, launch_soa_to_aos<L>(soa_or_field, (double *)h->staging, h->stride, dev_off + c0, n, h->s_main));
+				else launch_u_soa_to_aos(soa_or_field, (double *)h->staging, h->stride, ncomp, dev_off + c0, n, h->s_main);
+				CK(cudaMemcpyAsync(host.data(), h->staging, bytes, cudaMemcpyDeviceToHost, h->s_main));
+			}
+			CK(cudaStreamSynchronize(h->s_main));
+			if (fwrite(host.data(), 1, bytes, fh) != bytes) FAIL(LUMA_B200_EINVAL, "restart: short write");
+		}
+		else
+		{
+			if (fread(host.data(), 1, bytes, fh) != bytes) FAIL(LUMA_B200_EINVAL, "restart: file too short");
+			if (!soa) CK(cudaMemcpyAsync(soa_or_field + dev_off + c0, host.data(), bytes, cudaMemcpyHostToDevice, h->s_main));
+			else
+			{
+				CK(cudaMemcpyAsync(h->staging, host.data(), bytes, cudaMemcpyHostToDevice, h->s_main));
+				if (ncomp == h->Q) LAT(h->Q, launch_aos_to_soa<L>((const double *)h->staging, soa_or_field, h->stride, dev_off + c0, n, h->s_main));
+				else launch_u_aos_to_soa((const double *)h->staging, soa_or_field, h->stride, ncomp, dev_off + c0, n, h->s_main);
+			}
+			CK(cudaStreamSynchronize(h->s_main));
+		}
+		h->st.kernel_launches += soa ? 1 : 0;
+	}
+	return LUMA_B200_OK;
+}
+
+static int restart_fields(luma_b200_t *h, FILE *fh, bool write)
+{
+	int rc = restart_stream(h, fh, write, h->rho, 1, false);
+	if (rc == LUMA_B200_OK) rc = restart_stream(h, fh, write, h->u, h->D, true);
+	if (rc == LUMA_B200_OK) rc = restart_stream(h, fh, write, h->f[h->cur], h->Q, true);
+	if (rc == LUMA_B200_OK && h->tav)
+	{
+		rc = restart_stream(h, fh, write, h->tav, 1, false);
+		if (rc == LUMA_B200_OK) rc = restart_stream(h, fh, write, h->tav + (long long)1 * h->stride, h->D, true);
+		if (rc == LUMA_B200_OK) rc = restart_stream(h, fh, write, h->tav + (long long)(1 + h->D) * h->stride, 3 * h->D - 3, true);
+	}
+	return rc;
+}
+
+int luma_b200_restart_write(luma_b200_t *h, const char *path)
+{
+	if (!h || !path) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "restart_write before upload/init_synthetic");
+	CK(cudaSetDevice(h->p.device));
+	int rc = flush_steps(h);
+	if (rc) return rc;
+	FILE *fh = fopen(path, "wb");
+	if (!fh) FAIL(LUMA_B200_EINVAL, std::string("restart_write: cannot open ") + path);
+	RestartHeader hd;
+	memset(&hd, 0, sizeof(hd));
+	memcpy(hd.magic, "LUMAB2R1", 8);
+	hd.dims = h->D; hd.num_vels = h->Q; hd.N = h->p.N; hd.M = h->p.M; hd.K = h->p.K;
+	hd.x_offset = h->p.x_offset; hd.x_count = h->p.x_count; hd.t = h->t; hd.has_timeav = h->tav ? 1 : 0;
+	hd.omega = h->omega; hd.nu = h->nu;
+	rc = fwrite(&hd, sizeof(hd), 1, fh) == 1 ? LUMA_B200_OK : LUMA_B200_EINVAL;
+	if (rc == LUMA_B200_OK) rc = restart_fields(h, fh, true);
+	if (fclose(fh) != 0 && rc == LUMA_B200_OK) { h->err = "restart_write: close failed"; rc = LUMA_B200_EINVAL; }
+	return rc;
+}
+
+int luma_b200_restart_read(luma_b200_t *h, const char *path)
+{
+	if (!h || !path) return LUMA_B200_EINVAL;
+	if (!h->have_state) FAIL(LUMA_B200_ESTATE, "restart_read needs the geometry first (upload or init_synthetic)");
+	CK(cudaSetDevice(h->p.device));
+	// the state is replaced: steps accepted but not yet submitted are dropped, running ones are waited for
+	h->t_enq = h->t; h->timing_open = false; h->stats_dirty = false; h->prof_used = 0;
+	CK(cudaStreamSynchronize(h->s_comm));
+	CK(cudaStreamSynchronize(h->s_main));
+	h->stream_joined = true;
+	FILE *fh = fopen(path, "rb");
+	if (!fh) FAIL(LUMA_B200_EINVAL, std::string("restart_read: cannot open ") + path);
+	RestartHeader hd;
+	int rc = LUMA_B200_OK;
+	if (fread(&hd, sizeof(hd), 1, fh) != 1 || memcmp(hd.magic, "LUMAB2R1", 8) != 0) { h->err = "restart_read: not a luma_b200 restart file"; rc = LUMA_B200_EINVAL; }
+	else if (hd.dims != h->D || hd.num_vels != h->Q || hd.N != h->p.N || hd.M != h->p.M || hd.K != h->p.K ||
+		hd.x_offset != h->p.x_offset || hd.x_count != h->p.x_count || (hd.has_timeav != 0) != (h->tav != nullptr))
+	{ h->err = "restart_read: the file was written for another grid, slab or build (time averages)"; rc = LUMA_B200_EINVAL; }
+	if (rc == LUMA_B200_OK) rc = restart_fields(h, fh, false);
+	fclose(fh);
+	if (rc) return rc;
+	if (h->ghost)
+	{
+		rc = exchange_populations(h, h->f[h->cur], h->s_main);
+		if (rc) return rc;
+	}
+	CK(cudaMemcpyAsync(h->f[h->cur ^ 1], h->f[h->cur], (size_t)h->stride * h->Q * sizeof(double), cudaMemcpyDeviceToDevice, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	h->t = hd.t; h->t_enq = hd.t; h->omega = hd.omega; h->omega_enq = hd.omega; h->nu = hd.nu;
+	h->stepped = false;
+	return halo_health(h);
 }
 
 int luma_b200_download_lattyp(luma_b200_t *h, int32_t halo, int32_t *lattyp)

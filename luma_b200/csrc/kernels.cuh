@@ -20,7 +20,10 @@ struct StepArgs
 	int wrap_x;               // 1: periodic wrap inside the array (single rank); 0: ghost planes 0 and P-1
 	int p0, pstep;            // plane handled by blockIdx.y: p0 + blockIdx.y * pstep
 	int write_macro;          // store rho,u of fluid sites (last step of a call)
-	int use_tma;              // k_step_tma (loads staged through shared memory by bulk copies) instead of k_step
+	int use_tma;              // measured variants of k_step: 1 = k_step_tma (loads staged through shared memory by bulk copies),
+	                          // 2 = k_step_v2 (two sites per thread, 128-bit accesses); 0 = k_step
+	int rest_only;            // k_step: only the sites k_step_v2 left alone (its second launch)
+	int fill_holes;           // k_step: never-updated sites that share a 64-byte block with an updated site are copied through (see copy_through)
 	double omega;
 	double tau;               // 1.0 / omega
 	double smag_coef;         // 2.0*L_SQRT2*SQ(L_CSMAG)*L_RHOIN*SQ(cs)*SQ(cs)          optimised.cpp:752

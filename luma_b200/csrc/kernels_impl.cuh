@@ -299,22 +299,24 @@ __device__ __forceinline__ void tavg_update(const StepArgs &a, const long long i
 // ------------------------------------------------------------------------------------------------
 // the hot kernel: one thread per site of one x-plane; fluid sites only (optimised.cpp:91-156)
 // ------------------------------------------------------------------------------------------------
-template <class L, int COLL, int FORCE, bool TAVG, bool PEER>
-__device__ __forceinline__ void step_site(const StepArgs &a)
+// macro -> (time averages) -> equilibrium -> collide of one fluid site whose populations have been pulled into f;
+// leaves the post-collision populations in f and returns rho, u (optimised.cpp:122-156)
+template <class L, int COLL, int FORCE, bool TAVG>
+__device__ __forceinline__ void update_site(const StepArgs &a, const long long id, double (&f)[L::Q], double &rho, double (&u)[3])
 {
-	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
-	if (r >= a.MK) return;
-	const int p = a.p0 + (int)blockIdx.y * a.pstep;
-	const long long id = (long long)p * a.MK + r;
-	const uint32_t w = __ldg(a.cw + id);
-	if (cw_class<L>(w) != CLS_FLUID) return;
-
-	double f[L::Q], feq[L::Q], u[3], rho;
-	pull_populations<L>(a, p, r, id, w, f);
+	double feq[L::Q];
 	macroscopic<L, FORCE>(f, a.hFg, rho, u);
 	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
 	equilibrium_all<L>(rho, u, a.C, feq);
 	collide<L, COLL, FORCE>(a, id, u, feq, f);
+}
+
+template <class L, int COLL, int FORCE, bool TAVG, bool PEER>
+__device__ __forceinline__ void step_one(const StepArgs &a, const int p, const unsigned r, const long long id, const uint32_t w)
+{
+	double f[L::Q], u[3], rho;
+	pull_populations<L>(a, p, r, id, w, f);
+	update_site<L, COLL, FORCE, TAVG>(a, id, f, rho, u);
 	store_populations<L>(a, id, f);
 	if (PEER) store_outgoing<L>(a, p, r, f);
 	if (a.write_macro)
@@ -323,6 +325,107 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 #pragma unroll
 		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
 	}
+}
+
+// Pass-through copy of a never-updated site (eSolid, eRefined, non-regularised eVelocity): fout = fin at the site itself.
+// Semantically a no-op -- both lattices hold the same populations at such sites for the whole run (optimised.cpp:91-95
+// skips them and f.swap(fNew) :159 exchanges two arrays that agree there) -- but it turns the partially written 64-byte
+// blocks at the ends of a wall-bounded row (k = 0 solid, k = 1.. fluid) into full-block writes, which the memory system
+// handles without a read-modify-write.  Only done where it matters: the site shares an aligned 8-site block with a site
+// this kernel updates (StepArgs::fill_holes; measured in profiles/r02_variants.txt).
+template <class L>
+__device__ __forceinline__ void copy_through(const StepArgs &a, const long long id)
+{
+	const char *pi = reinterpret_cast<const char *>(a.fin + id);
+	char *po = reinterpret_cast<char *>(a.fout + id);
+	const long long sb = a.stride * (long long)sizeof(double);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+		*reinterpret_cast<double *>(po + (long long)v * sb) = load_pop(reinterpret_cast<const double *>(pi + (long long)v * sb));
+}
+
+template <class L, int COLL, int FORCE, bool TAVG, bool PEER>
+__device__ __forceinline__ void step_site(const StepArgs &a)
+{
+	const unsigned r = blockIdx.x * STEP_THREADS + threadIdx.x;
+	const bool inside = r < a.MK;
+	const int p = a.p0 + (int)blockIdx.y * a.pstep;
+	const long long id = (long long)p * a.MK + r;
+	const uint32_t w = inside ? __ldg(a.cw + id) : 0u;
+	const bool fluid = inside && cw_class<L>(w) == CLS_FLUID;
+#ifdef __CUDACC__
+	if (a.fill_holes)
+	{
+		const unsigned updated = __ballot_sync(0xffffffffu, fluid);
+		if (inside && !fluid && w == 0u && ((updated >> (threadIdx.x & 24u)) & 0xffu) != 0u) copy_through<L>(a, id);
+	}
+#endif
+	if (!fluid) return;
+	if (a.rest_only)
+	{
+		// second launch of the two-sites-per-thread variant: only the sites whose pair (r & ~1, r | 1) k_step_v2 left alone
+		const uint32_t wp = __ldg(a.cw + (id ^ 1));
+		const bool x_wraps = a.wrap_x && (p == 0 || p == a.P - 1);
+		if (!x_wraps && (w & (CW<L>::LINKS | CW<L>::EDGE)) == 0 && cw_class<L>(wp) == CLS_FLUID && (wp & (CW<L>::LINKS | CW<L>::EDGE)) == 0) return;
+	}
+	step_one<L, COLL, FORCE, TAVG, PEER>(a, p, r, id, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant of k_step with TWO z-adjacent sites per thread and 128-bit accesses (LUMA_B200_V2=1; measured against the
+// one-site kernel in profiles/r02_variants.txt).  Sites (r, r+1), r even: all Q stores and the loads of the populations
+// with c_z = 0 are aligned 16-byte accesses (STG.128 / LDG.128); the populations with c_z = +-1 are pulled from an odd
+// element offset, where a 16-byte access would be misaligned, and stay two 8-byte loads.  A pair takes this path only if
+// both sites are plain fluid sites away from walls and array edges; everything else is left to a second launch of the
+// one-site kernel (StepArgs::rest_only).
+// ------------------------------------------------------------------------------------------------
+#ifndef LUMA_MIN_BLOCKS_V2
+#define LUMA_MIN_BLOCKS_V2 3
+#endif
+template <class L, int COLL, int FORCE, bool TAVG>
+__global__ void __launch_bounds__(STEP_THREADS, LUMA_MIN_BLOCKS_V2) k_step_v2(const StepArgs a)
+{
+#ifdef __CUDACC__
+	const unsigned r = 2u * (blockIdx.x * STEP_THREADS + threadIdx.x);
+	if (r >= a.MK) return;
+	const int p = a.p0 + (int)blockIdx.y * a.pstep;
+	const long long id = (long long)p * a.MK + r;
+	const uint2 ww = __ldg(reinterpret_cast<const uint2 *>(a.cw + id));
+	const bool x_wraps = a.wrap_x && (p == 0 || p == a.P - 1);
+	const bool plain0 = cw_class<L>(ww.x) == CLS_FLUID && (ww.x & (CW<L>::LINKS | CW<L>::EDGE)) == 0;
+	const bool plain1 = cw_class<L>(ww.y) == CLS_FLUID && (ww.y & (CW<L>::LINKS | CW<L>::EDGE)) == 0;
+	if (plain0 && plain1 && !x_wraps)
+	{
+		double fa[L::Q], fb[L::Q], ua[3], ub[3], rhoa, rhob;
+		const char *pb = reinterpret_cast<const char *>(a.fin + id);
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v)
+		{
+			if (L::c(v, 2) == 0)
+			{
+				const double2 t = __ldg(reinterpret_cast<const double2 *>(pb + a.off_pull[v]));
+				fa[v] = t.x; fb[v] = t.y;
+			}
+			else
+			{
+				fa[v] = load_pop(reinterpret_cast<const double *>(pb + a.off_pull[v]));
+				fb[v] = load_pop(reinterpret_cast<const double *>(pb + a.off_pull[v] + 8));
+			}
+		}
+		update_site<L, COLL, FORCE, TAVG>(a, id, fa, rhoa, ua);
+		update_site<L, COLL, FORCE, TAVG>(a, id + 1, fb, rhob, ub);
+		char *po = reinterpret_cast<char *>(a.fout + id);
+		const long long sb = a.stride * (long long)sizeof(double);
+#pragma unroll
+		for (int v = 0; v < L::Q; ++v) *reinterpret_cast<double2 *>(po + (long long)v * sb) = make_double2(fa[v], fb[v]);
+		if (a.write_macro)
+		{
+			*reinterpret_cast<double2 *>(a.rho + id) = make_double2(rhoa, rhob);
+#pragma unroll
+			for (int d = 0; d < L::D; ++d) *reinterpret_cast<double2 *>(a.u + (long long)d * a.stride + id) = make_double2(ua[d], ub[d]);
+		}
+	}
+#endif
 }
 
 template <class L, int COLL, int FORCE, bool TAVG>
@@ -419,7 +522,7 @@ __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_st
 	}
 	if (!live || cw_class<L>(w) != CLS_FLUID) return;
 
-	double f[L::Q], feq[L::Q], u[3], rho;
+	double f[L::Q], u[3], rho;
 	if (staged && (w & (CW<L>::LINKS | CW<L>::EDGE)) == 0)
 	{
 		// parity of the shifted start == parity of c_z when M*K and K are even (checked by the launcher)
@@ -427,10 +530,7 @@ __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_st
 		for (int v = 0; v < L::Q; ++v) f[v] = tile[v][threadIdx.x + ((L::c(v, 2) != 0) ? 1 : 0)];
 	}
 	else pull_populations<L>(a, p, r, id, w, f);
-	macroscopic<L, FORCE>(f, a.hFg, rho, u);
-	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
-	equilibrium_all<L>(rho, u, a.C, feq);
-	collide<L, COLL, FORCE>(a, id, u, feq, f);
+	update_site<L, COLL, FORCE, TAVG>(a, id, f, rho, u);
 	store_populations<L>(a, id, f);
 	if (a.write_macro)
 	{
@@ -739,7 +839,20 @@ template <class L> void launch_step(const StepArgs &a, int coll, int force, int 
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
 	// the TMA-staged variant needs even M*K and K (16-byte aligned bulk copies) and the start of a tile on an even element
-	if (a.use_tma && (a.MK & 1u) == 0 && (a.K & 1) == 0) LUMA_DISPATCH(k_step_tma, grid, STEP_THREADS);
+	if (a.use_tma == 1 && (a.MK & 1u) == 0 && (a.K & 1) == 0) LUMA_DISPATCH(k_step_tma, grid, STEP_THREADS);
+	else if (a.use_tma == 2 && (a.MK & 1u) == 0 && (a.K & 1) == 0 && L::D == 3)
+	{
+		// two sites per thread: half as many threads per plane
+		dim3 grid2((a.MK / 2 + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
+		LUMA_DISPATCH(k_step_v2, grid2, STEP_THREADS);
+		StepArgs rest = a;
+		rest.rest_only = 1;
+		{
+			const StepArgs &a = rest;
+			LUMA_DISPATCH(k_step, grid, STEP_THREADS);
+		}
+		if (launches) ++*launches;
+	}
 	else LUMA_DISPATCH(k_step, grid, STEP_THREADS);
 	if (launches) ++*launches;
 }

@@ -10,6 +10,7 @@ shim makes -- so these Python classes are the reference-facing API used by tests
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -209,6 +210,14 @@ class GridObj:
     def upload_timeav(self, rho_timeav=None, ui_timeav=None, uiuj_timeav=None):
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (rho_timeav, ui_timeav, uiuj_timeav)]
         capi.check(self._L.luma_b200_upload_timeav(self._h, 0, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2])), self._h)
+
+    def io_restart_write(self, path: str):
+        """Binary restart file of this rank's state (GridObj::io_restart(eWrite), src/GridObj_ops_io.cpp:406)."""
+        capi.check(self._L.luma_b200_restart_write(self._h, os.fsencode(path)), self._h)
+
+    def io_restart_read(self, path: str):
+        """Replace t, f, rho, u (and the time averages) by a restart file's (GridObj::io_restart(eRead), :519)."""
+        capi.check(self._L.luma_b200_restart_read(self._h, os.fsencode(path)), self._h)
 
     def computeLiftDrag(self):
         """Momentum-exchange force on bounce-back bodies of the last step (this rank's share)."""

@@ -21,7 +21,7 @@ def defs(case, res):
 
 
 def run(case, res, steps, env=None):
-    for k in ("LUMA_B200_TMA", "LUMA_B200_STRIDE_PAD"):
+    for k in ("LUMA_B200_TMA", "LUMA_B200_V2", "LUMA_B200_STRIDE_PAD", "LUMA_B200_FILL"):
         os.environ.pop(k, None)
     os.environ.update(env or {})
     g = E.GridObj(defs(case, res)).LBM_initGrid()
@@ -45,7 +45,25 @@ def run(case, res, steps, env=None):
 
 
 if __name__ == "__main__":
-    quick = len(sys.argv) > 1
+    mode = sys.argv[1] if len(sys.argv) > 1 else "full"
+    if mode == "lib":           # one tuning-variant library (LUMA_B200_LIB), the two cases that matter
+        print("== library:", os.environ.get("LUMA_B200_LIB", "default"), flush=True)
+        for res, st in ((256, 300), (384, 100)):
+            for case in ("cavity", "channel_f", "channel_s"):
+                run(case, res, st)
+        sys.exit(0)
+    if mode == "v2":            # the two measured kernel variants against the default kernel
+        for res, st in ((256, 300), (384, 100), (512, 40)):
+            for case in ("cavity", "box", "channel", "channel_f", "channel_s"):
+                run(case, res, st)
+                run(case, res, st, {"LUMA_B200_FILL": "1"})
+                run(case, res, st, {"LUMA_B200_V2": "1"})
+                run(case, res, st, {"LUMA_B200_TMA": "1"})
+        sys.exit(0)
+    if mode == "one":           # a single configuration (for ncu): one <case> <res> [ENV=VALUE ...]
+        run(sys.argv[2], int(sys.argv[3]), 20, dict(kv.split("=", 1) for kv in sys.argv[4:]))
+        sys.exit(0)
+    quick = mode == "quick"
     for res in (256, 384, 512):
         st = {256: 300, 384: 100, 512: 40}[res]
         for case in ("cavity", "box", "channel", "channel_f", "channel_s"):

@@ -68,15 +68,14 @@ def main():
         Q, D, N, MK = case.Q, case.dims, case.N, case.M * case.K
         # both state paths and both transports, one handle (= one NCCL communicator bootstrap) each
         # three transports: peer stores by the copy kernel, NCCL send/recv, peer stores fused into the face kernels' epilogue
-        modes = ("device_init", "upload+nccl", "device_init+fused")
+        modes = ("device_init+fused", "upload+nccl", "device_init+copy")
         if os.environ.get("LUMA_TEST_NO_FUSED"):
-            modes = modes[:2]
+            modes = modes[1:]
         for mode in modes:
             uid = ring.broadcast_unique_id(dist, rank)      # one ncclUniqueId per communicator / handle
             g = luma_b200.GridObj(defs, rank=rank, nranks=world, device=local, unique_id=uid)
             if not mode.endswith("+nccl"):
-                if mode.endswith("+fused"):
-                    os.environ["LUMA_B200_FUSED_HALO"] = "1"    # read by luma_b200_p2p_attach
+                os.environ["LUMA_B200_FUSED_HALO"] = "1" if mode.endswith("+fused") else "0"    # read by luma_b200_p2p_attach
                 attached = ring.attach_p2p(dist, g, rank, world)       # device-initiated halo exchange; "+nccl" keeps send/recv
                 os.environ.pop("LUMA_B200_FUSED_HALO", None)
                 assert attached, "no CUDA IPC peer mapping between ring neighbours on this box"

@@ -315,9 +315,9 @@ def test_parity_at_size(name, path):
 @pytest.mark.parametrize("name", ["cav3d_32", "cyl3d", "chan3d", "tunnel2d", "cyl2d_tav", "kbc2d_cyl"])
 def test_upload_without_populations_equals_full_upload(name):
     """f_aos = NULL (f = feq(rho,u) evaluated on the device) leaves exactly the state a full upload leaves, for the
-    L_NO_FLOW cases where the host's f is feq(rho,u) at t = 0"""
+    cases where the host's f is feq(rho,u) at t = 0: L_NO_FLOW builds, or no body labelled after LBM_initGrid"""
     case = CASES[name]
-    assert case.no_flow
+    assert case.no_flow or case.box is None
     ref = port.PortGrid(case)
     a = luma_b200.GridObj(defs_from_case(case))
     a.upload(None, ref.rho, ref.u, ref.lattyp, ref.uin(0), ref.uin(1), ref.uin(2))
@@ -363,8 +363,36 @@ def test_stats_window_covers_the_steps_between_read_points():
     g.LBM_multi_opt(50)
     st = g.stats()
     assert st["steps"] == 50 and st["ms_last_call"] > 0
-    assert abs(st["ms_per_step"] * 50 - st["ms_last_call"]) < 1e-9 * max(1.0, st["ms_last_call"])
+    assert abs(st["ms_per_step"] * 50 - st["ms_last_call"]) < 1e-6 * max(1.0, st["ms_last_call"])
     g.LBM_multi_opt(20)
     st2 = g.stats()
-    assert st2["steps"] == 70 and abs(st2["ms_per_step"] * 20 - st2["ms_last_call"]) < 1e-9 * max(1.0, st2["ms_last_call"])
+    assert st2["steps"] == 70 and abs(st2["ms_per_step"] * 20 - st2["ms_last_call"]) < 1e-6 * max(1.0, st2["ms_last_call"])
     g.close()
+
+
+@pytest.mark.parametrize("name", ["cyl3d", "cyl2d_tav", "cav2d_reramp", "kbc2d_cyl"])
+def test_binary_restart_round_trip_continues_bitwise(name, tmp_path):
+    """luma_b200_restart_write after 13 steps, luma_b200_restart_read into a NEW handle whose geometry came from the fresh host
+    state (upload without populations), then 20 more steps: bit-identical to the oracle's uninterrupted run -- fields, time
+    averages, t and the Reynolds-ramp omega"""
+    case = CASES[name]
+    ref = port.PortGrid(case)
+    init = {nm: np.array(getattr(ref, nm)) for nm in ("f", "rho", "u", "lattyp")}
+    a = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    a.LBM_multi_opt(13); ref.step(13)
+    path = str(tmp_path / "restart_rank0.bin")
+    a.io_restart_write(path)
+    a.close()
+    b = luma_b200.GridObj(defs_from_case(case))
+    b.upload(init["f"], init["rho"], init["u"], init["lattyp"], ref.uin(0), ref.uin(1), ref.uin(2))
+    b.io_restart_read(path)
+    assert b.t == 13 and b.omega == ref.omega
+    _assert_same(name, "restart t13", b.download(), ref, b)
+    b.LBM_multi_opt(20); ref.step(20)
+    assert b.t == ref.t and b.omega == ref.omega
+    _assert_same(name, "restart t33", b.download(), ref, b)
+    # a file written for another grid is refused
+    other = luma_b200.GridObj(defs_from_case(CASES["cav2d_64"])).LBM_initGrid()
+    with pytest.raises(capi.LumaB200Error):
+        other.io_restart_read(path)
+    other.close(); b.close(); ref.close()
