@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 #include <dlfcn.h>
@@ -106,6 +107,8 @@ struct luma_b200
 	double *tav = nullptr;          // time-averaged statistics, SoA [1 + D + 3D-3][stride]
 	void *staging = nullptr;
 	size_t staging_bytes = 0;
+	uint8_t *types_host = nullptr;  // pinned host mirror of `types` (geometry finalisation)
+	size_t types_host_bytes = 0;
 	double *momex_dev = nullptr;
 	cudaStream_t s_main = nullptr, s_comm = nullptr, s_copy = nullptr;
 	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_int = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_snap = nullptr, ev_copied = nullptr,
@@ -139,7 +142,7 @@ struct luma_b200
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
 	int geometry_epoch = 0;         // bumped by upload / init_synthetic
-	bool fill_holes = false;        // LUMA_B200_FILL=1: copy never-updated sites through where they share a 64-byte block with updated ones
+	bool fill_holes = true;         // solid sites at wall-bounded row ends join the stores of their sector (LUMA_B200_FILL=0 turns it off)
 	int use_tma = 0;                // LUMA_B200_TMA=1 / LUMA_B200_V2=1 at create: measured variants of k_step (profiles/r02_variants.txt)
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
@@ -282,6 +285,7 @@ static void free_all(luma_b200_t *h)
 	cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->cw); cudaFree(h->bcdesc); cudaFree(h->types);
 	cudaFree(h->rho); cudaFree(h->u); cudaFree(h->uin); cudaFree(h->bc_list); cudaFree(h->staging); cudaFree(h->momex_dev);
 	cudaFree(h->bc_extra); cudaFree(h->vel_list); cudaFree(h->tav);
+	if (h->types_host) cudaFreeHost(h->types_host);
 	if (h->ev_edge) cudaEventDestroy(h->ev_edge);
 	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -355,7 +359,7 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 		const char *tv = getenv("LUMA_B200_TMA"), *v2 = getenv("LUMA_B200_V2");
 		h->use_tma = (tv && *tv && atoi(tv) != 0) ? 1 : ((v2 && *v2 && atoi(v2) != 0) ? 2 : 0);
 		const char *fv = getenv("LUMA_B200_FILL");
-		h->fill_holes = fv && *fv && atoi(fv) != 0;
+		h->fill_holes = !(fv && *fv && atoi(fv) == 0);
 	}
 
 	int ndev = 0;
@@ -659,8 +663,17 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 		int rc = exchange_ghost_planes(h, h->s_main);
 		if (rc) return rc;
 	}
-	std::vector<uint8_t> types((size_t)h->cells + 8, 0);
-	CK(cudaMemcpyAsync(types.data(), h->types, (size_t)h->cells, cudaMemcpyDeviceToHost, h->s_main));
+	// host mirror of the eType array: pinned (the copy runs at PCIe speed), kept for later uploads
+	if (h->types_host_bytes < (size_t)h->cells + 8)
+	{
+		if (h->types_host) cudaFreeHost(h->types_host);
+		h->types_host = nullptr; h->types_host_bytes = 0;
+		if (cudaHostAlloc((void **)&h->types_host, (size_t)h->cells + 8, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); FAIL(LUMA_B200_ENOMEM, "host mirror of the eType array"); }
+		h->types_host_bytes = (size_t)h->cells + 8;
+	}
+	uint8_t *types = h->types_host;
+	memset(types + h->cells, 0, 8);
+	CK(cudaMemcpyAsync(types, h->types, (size_t)h->cells, cudaMemcpyDeviceToHost, h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
 
 	const int P = h->P, M = p.M, K = p.K, Q = h->Q, D = h->D;
@@ -669,16 +682,28 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 	auto site = [&](int pl, int j, int k) { return ((long long)pl * M + j) * K + k; };
 	auto never_streamed = [&](uint8_t t) { return t == T_SOLID || t == T_REFINED || (t == T_VELOCITY && !reg); };   // optimised.cpp:91-95
 
-	std::vector<long long> list;                 // sites k_bc handles
-	std::vector<long long> forced;               // eFluid sites that must be handled per link (class 4)
-	std::vector<std::pair<long long, int>> extra; // (site, extra advances of its time averages per step)
-	std::vector<long long> vel;                  // forced-equilibrium eVelocity sites (their stored u follows the ramp)
-	bool general = false;
-
-	for (int pl = 0; pl < P; ++pl)
+	// The scan over all sites runs on a few host threads, each over a contiguous range of planes; the per-range results are
+	// concatenated in plane order (lists stay ascending) and the first failure in plane order is the one reported.
+	struct ScanOut
+	{
+		std::vector<long long> list;                 // sites k_bc handles
+		std::vector<long long> forced;               // eFluid sites that must be handled per link (class 4)
+		std::vector<std::pair<long long, int>> extra; // (site, extra advances of its time averages per step)
+		std::vector<long long> vel;                  // forced-equilibrium eVelocity sites (their stored u follows the ramp)
+		bool general = false;
+		int rc = LUMA_B200_OK;
+		std::string err;
+	};
+	auto scan_planes = [&](const int pl_begin, const int pl_end, ScanOut &o) -> int
+	{
+	std::vector<long long> &list = o.list, &forced = o.forced, &vel = o.vel;
+	std::vector<std::pair<long long, int>> &extra = o.extra;
+	bool &general = o.general;
+#define SCAN_FAIL(code, msg) do { o.err = (msg); o.rc = (code); return (code); } while (0)
+	for (int pl = pl_begin; pl < pl_end; ++pl)
 	{
 		const bool owned = pl >= pb && pl < pe;
-		const uint8_t *row = &types[(size_t)pl * M * K];
+		const uint8_t *row = types + (size_t)pl * M * K;
 		for (int j = 0; j < M; ++j)
 			for (int k = 0; k < K; ++k)
 			{
@@ -693,7 +718,7 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 				if (t == T_SOLID || t == T_FLUID) continue;
 				const long long id = site(pl, j, k);
 				if (t != T_VELOCITY && t != T_PRESSURE && t != T_SLIP && t != T_EXTRAPOLATE_RIGHT)
-					FAIL(LUMA_B200_EUNSUPPORTED, "site type " + std::to_string((int)t) + " (refinement/BFL) is outside the level-0 path");
+					SCAN_FAIL(LUMA_B200_EUNSUPPORTED, "site type " + std::to_string((int)t) + " (refinement/BFL) is outside the level-0 path");
 
 				// sites that pull from an eExtrapolateRight or forced-equilibrium eVelocity site take the per-link path
 				if (t == T_EXTRAPOLATE_RIGHT || (t == T_VELOCITY && !reg))
@@ -710,8 +735,8 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 						if (t == T_EXTRAPOLATE_RIGHT && pl - 2 < pb)
 						{
 							// optimised.cpp:249-250 reads two planes to the left of the source
-							if (h->ghost) FAIL(LUMA_B200_EUNSUPPORTED, "an eExtrapolateRight site needs two planes to its left inside the same slab (slab too thin, or the site is reached through the periodic wrap)");
-							FAIL(LUMA_B200_EBC_OFFGRID, "eExtrapolateRight site within two planes of the low x end: the reference reads off the array");
+							if (h->ghost) SCAN_FAIL(LUMA_B200_EUNSUPPORTED, "an eExtrapolateRight site needs two planes to its left inside the same slab (slab too thin, or the site is reached through the periodic wrap)");
+							SCAN_FAIL(LUMA_B200_EBC_OFFGRID, "eExtrapolateRight site within two planes of the low x end: the reference reads off the array");
 						}
 						if (dt == T_FLUID) forced.push_back(site(dp, dj, dk));
 					}
@@ -722,7 +747,7 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 				{
 					general = true;
 					if ((desc_of(id, pl, j, k) >> CW_EC_SHIFT) == 0)
-						FAIL(LUMA_B200_EBC_NOT_WALL, "Slip wall not located inside a domain wall region. Not currently supported.");   // optimised.cpp:577
+						SCAN_FAIL(LUMA_B200_EBC_NOT_WALL, "Slip wall not located inside a domain wall region. Not currently supported.");   // optimised.cpp:577
 					list.push_back(id);
 					continue;
 				}
@@ -738,8 +763,8 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 				// regularised velocity / pressure site (optimised.cpp:313-510)
 				const uint32_t d = desc_of(id, pl, j, k);
 				const int ec = (int)(d >> CW_EC_SHIFT);
-				if (ec == 0) FAIL(LUMA_B200_EBC_NOT_WALL, luma_b200_strerror(LUMA_B200_EBC_NOT_WALL));
-				if (ec > 1 && t == T_PRESSURE) FAIL(LUMA_B200_EBC_PRESSURE_EDGE, luma_b200_strerror(LUMA_B200_EBC_PRESSURE_EDGE));
+				if (ec == 0) SCAN_FAIL(LUMA_B200_EBC_NOT_WALL, luma_b200_strerror(LUMA_B200_EBC_NOT_WALL));
+				if (ec > 1 && t == T_PRESSURE) SCAN_FAIL(LUMA_B200_EBC_PRESSURE_EDGE, luma_b200_strerror(LUMA_B200_EBC_PRESSURE_EDGE));
 				if (ec > 1 || t == T_PRESSURE)
 				{
 					int n[3];
@@ -749,25 +774,55 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 					{
 						const int gi = p.x_offset + (pl - h->ghost) + m * n[0], jj = j + m * n[1], kk = k + m * n[2];
 						if (gi < 0 || gi >= p.N || jj < 0 || jj >= M || kk < 0 || kk >= K)
-							FAIL(LUMA_B200_EBC_OFFGRID, luma_b200_strerror(LUMA_B200_EBC_OFFGRID));
+							SCAN_FAIL(LUMA_B200_EBC_OFFGRID, luma_b200_strerror(LUMA_B200_EBC_OFFGRID));
 						const int pp = pl + m * n[0];
 						if (pp < pb || pp >= pe)
-							FAIL(LUMA_B200_EUNSUPPORTED, "slab too thin: a boundary site extrapolates from a plane owned by another rank");
+							SCAN_FAIL(LUMA_B200_EUNSUPPORTED, "slab too thin: a boundary site extrapolates from a plane owned by another rank");
 						const long long idn = site(pp, jj, kk);
 						const uint8_t tn = types[(size_t)idn];
 						if (tn != T_SOLID && tn != T_FLUID)
-							FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from another boundary site (loop-order dependent in the reference)");
+							SCAN_FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from another boundary site (loop-order dependent in the reference)");
 						if (idn > id)
 						{
 							// the reference streams + macros this neighbour early (optimised.cpp:1375-1404)
 							if (tn == T_SOLID)
-								FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from an eSolid site with a larger index (the reference streams into that solid site)");
+								SCAN_FAIL(LUMA_B200_EUNSUPPORTED, "a boundary site extrapolates from an eSolid site with a larger index (the reference streams into that solid site)");
 							if (p.time_averaged) { extra.push_back({ idn, ncalls }); forced.push_back(idn); }
 						}
 					}
 				}
 				list.push_back(id);
 			}
+	}
+	return LUMA_B200_OK;
+#undef SCAN_FAIL
+	};
+	int nthreads = 1;
+	if (h->cells > (4LL << 20))
+	{
+		nthreads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+		nthreads = std::min(nthreads, P);
+	}
+	std::vector<ScanOut> parts((size_t)nthreads);
+	if (nthreads == 1) scan_planes(0, P, parts[0]);
+	else
+	{
+		std::vector<std::thread> pool;
+		for (int th = 0; th < nthreads; ++th)
+			pool.emplace_back([&, th] { scan_planes((int)((long long)P * th / nthreads), (int)((long long)P * (th + 1) / nthreads), parts[(size_t)th]); });
+		for (std::thread &t : pool) t.join();
+	}
+	std::vector<long long> list, forced, vel;
+	std::vector<std::pair<long long, int>> extra;
+	bool general = false;
+	for (ScanOut &o : parts)
+	{
+		if (o.rc) FAIL(o.rc, o.err);
+		list.insert(list.end(), o.list.begin(), o.list.end());
+		forced.insert(forced.end(), o.forced.begin(), o.forced.end());
+		extra.insert(extra.end(), o.extra.begin(), o.extra.end());
+		vel.insert(vel.end(), o.vel.begin(), o.vel.end());
+		general = general || o.general;
 	}
 
 	// class-4 fluid sites join the list; the list is kept in ascending site order

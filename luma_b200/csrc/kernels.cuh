@@ -23,7 +23,7 @@ struct StepArgs
 	int use_tma;              // measured variants of k_step: 1 = k_step_tma (loads staged through shared memory by bulk copies),
 	                          // 2 = k_step_v2 (two sites per thread, 128-bit accesses); 0 = k_step
 	int rest_only;            // k_step: only the sites k_step_v2 left alone (its second launch)
-	int fill_holes;           // k_step: never-updated sites that share a 64-byte block with an updated site are copied through (see copy_through)
+	int fill_holes;           // k_step: never-updated sites that share a 32-byte sector with an updated site join its stores (see step_site)
 	double omega;
 	double tau;               // 1.0 / omega
 	double smag_coef;         // 2.0*L_SQRT2*SQ(L_CSMAG)*L_RHOIN*SQ(cs)*SQ(cs)          optimised.cpp:752

@@ -327,23 +327,13 @@ __device__ __forceinline__ void step_one(const StepArgs &a, const int p, const u
 	}
 }
 
-// Pass-through copy of a never-updated site (eSolid, eRefined, non-regularised eVelocity): fout = fin at the site itself.
-// Semantically a no-op -- both lattices hold the same populations at such sites for the whole run (optimised.cpp:91-95
-// skips them and f.swap(fNew) :159 exchanges two arrays that agree there) -- but it turns the partially written 64-byte
-// blocks at the ends of a wall-bounded row (k = 0 solid, k = 1.. fluid) into full-block writes, which the memory system
-// handles without a read-modify-write.  Only done where it matters: the site shares an aligned 8-site block with a site
-// this kernel updates (StepArgs::fill_holes; measured in profiles/r02_variants.txt).
-template <class L>
-__device__ __forceinline__ void copy_through(const StepArgs &a, const long long id)
-{
-	const char *pi = reinterpret_cast<const char *>(a.fin + id);
-	char *po = reinterpret_cast<char *>(a.fout + id);
-	const long long sb = a.stride * (long long)sizeof(double);
-#pragma unroll
-	for (int v = 0; v < L::Q; ++v)
-		*reinterpret_cast<double *>(po + (long long)v * sb) = load_pop(reinterpret_cast<const double *>(pi + (long long)v * sb));
-}
-
+// Pass-through of never-updated sites (eSolid, eRefined, non-regularised eVelocity) that share a 32-byte sector with a site
+// this kernel updates -- the solid site at each end of a wall-bounded z-row: k = 0 solid, k = 1, 2, 3 fluid.  Without it the
+// warp's store covers 24 of the sector's 32 bytes, and the L2 has to fetch the sector from DRAM to rebuild its ECC (ncu:
+// lts__t_sectors_data_ecc = 2 sectors x rows x Q per step, 7-9 % of the step on walls in z, profiles/r02_probe_walls.txt).
+// With it the solid site's lane joins the SAME store instructions with its own populations (fout = fin at the site itself), and
+// every sector is written whole.  Semantically a no-op: both lattices hold the same populations at such sites for the whole
+// run (optimised.cpp:91-95 skips them and f.swap(fNew) :159 exchanges two arrays that agree there).
 template <class L, int COLL, int FORCE, bool TAVG, bool PEER>
 __device__ __forceinline__ void step_site(const StepArgs &a)
 {
@@ -353,22 +343,39 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 	const long long id = (long long)p * a.MK + r;
 	const uint32_t w = inside ? __ldg(a.cw + id) : 0u;
 	const bool fluid = inside && cw_class<L>(w) == CLS_FLUID;
+	bool through = false;
 #ifdef __CUDACC__
 	if (a.fill_holes)
 	{
 		const unsigned updated = __ballot_sync(0xffffffffu, fluid);
-		if (inside && !fluid && w == 0u && ((updated >> (threadIdx.x & 24u)) & 0xffu) != 0u) copy_through<L>(a, id);
+		through = inside && !fluid && w == 0u && ((updated >> (threadIdx.x & 28u)) & 0xfu) != 0u;
 	}
 #endif
-	if (!fluid) return;
+	if (!fluid && !through) return;
 	if (a.rest_only)
 	{
 		// second launch of the two-sites-per-thread variant: only the sites whose pair (r & ~1, r | 1) k_step_v2 left alone
 		const uint32_t wp = __ldg(a.cw + (id ^ 1));
 		const bool x_wraps = a.wrap_x && (p == 0 || p == a.P - 1);
+		if (!fluid) return;
 		if (!x_wraps && (w & (CW<L>::LINKS | CW<L>::EDGE)) == 0 && cw_class<L>(wp) == CLS_FLUID && (wp & (CW<L>::LINKS | CW<L>::EDGE)) == 0) return;
 	}
-	step_one<L, COLL, FORCE, TAVG, PEER>(a, p, r, id, w);
+	double f[L::Q], u[3], rho;
+	if (fluid)
+	{
+		pull_populations<L>(a, p, r, id, w, f);
+		update_site<L, COLL, FORCE, TAVG>(a, id, f, rho, u);
+	}
+	else load_own<L>(a, id, f);
+	store_populations<L>(a, id, f);
+	if (!fluid) return;
+	if (PEER) store_outgoing<L>(a, p, r, f);
+	if (a.write_macro)
+	{
+		a.rho[id] = rho;
+#pragma unroll
+		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
+	}
 }
 
 // ------------------------------------------------------------------------------------------------

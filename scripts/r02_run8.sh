@@ -6,7 +6,7 @@
 # Independent runs share the box on disjoint GPU sets (CUDA_VISIBLE_DEVICES) to keep the lease short.
 set -x
 mkdir -p gpurun_out
-HALO=${HALO:-p2p}
+HALO=${HALO:-fused}
 W=tests/mgpu_worker.py
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 C8="chan3d,cyl3d,chan2d,cyl2d,slipchan3d,sliptunnel2d,sliptunnel3d,fevel2d,fevel3d,fevel2d_tav,tunnel2d_tav"
