@@ -131,6 +131,35 @@ __device__ __forceinline__ void load_own(const StepArgs &a, const long long id, 
 	for (int v = 0; v < L::Q; ++v) fo[v] = load_pop(reinterpret_cast<const double *>(pb + (long long)v * sb));
 }
 
+// The pull of a whole warp of step_site, arranged so that a wall next to the warp does not split it: when no lane needs a
+// periodic wrap, every lane -- plain fluid sites, sites with bounce-back links, and the never-updated sites that only complete
+// a sector (`through`) -- takes ONE load sequence whose per-population offset is selected without a branch:
+//     pulled population (kernel-uniform offset)  |  own opposite population (bounce-back)  |  own population (pass-through).
+// Warps without links or pass-through lanes keep the pure kernel-uniform sequence; lanes on the first/last row or column
+// (periodic wrap) or on a wrapping x-plane use the general pull_populations.  (`mode` is warp-uniform: 0 pure, 1 select.)
+template <class L>
+__device__ __forceinline__ void pull_warp(const StepArgs &a, const int p, const unsigned r, const long long id, const uint32_t w,
+	const bool fluid, const bool through, const int mode, double (&f)[L::Q])
+{
+	const bool x_wraps = a.wrap_x && (p == 0 || p == a.P - 1);
+	if (mode == 0 || (w & CW<L>::EDGE) != 0 || x_wraps)
+	{
+		if (fluid) pull_populations<L>(a, p, r, id, w, f);
+		else load_own<L>(a, id, f);
+		return;
+	}
+	const char *pb = reinterpret_cast<const char *>(a.fin + id);
+	const long long sb = a.stride * (long long)sizeof(double);
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		long long off = a.off_pull[v];
+		if (v < L::Q - 1 && ((w >> v) & 1u)) off = (long long)opposite<L>(v) * sb;
+		if (through) off = (long long)v * sb;
+		f[v] = load_pop(reinterpret_cast<const double *>(pb + off));
+	}
+}
+
 // BGK(/Smagorinsky) collision with optional Guo forcing, GridObj::_LBM_collide_opt (optimised.cpp:765-790),
 // or the KBC operator _LBM_kbcCollide_opt (:1122-1305), which replaces f by the collided own-site populations
 template <class L, int COLL, int FORCE>
@@ -344,11 +373,14 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 	const uint32_t w = inside ? __ldg(a.cw + id) : 0u;
 	const bool fluid = inside && cw_class<L>(w) == CLS_FLUID;
 	bool through = false;
+	int mode = 0;
 #ifdef __CUDACC__
 	if (a.fill_holes)
 	{
 		const unsigned updated = __ballot_sync(0xffffffffu, fluid);
 		through = inside && !fluid && w == 0u && ((updated >> (threadIdx.x & 28u)) & 0xfu) != 0u;
+		// warp-uniform: does any lane have a bounce-back link or complete a sector?  then all lanes take the select sequence
+		mode = __any_sync(0xffffffffu, through || (fluid && (w & CW<L>::LINKS) != 0)) ? 1 : 0;
 	}
 #endif
 	if (!fluid && !through) return;
@@ -361,12 +393,8 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 		if (!x_wraps && (w & (CW<L>::LINKS | CW<L>::EDGE)) == 0 && cw_class<L>(wp) == CLS_FLUID && (wp & (CW<L>::LINKS | CW<L>::EDGE)) == 0) return;
 	}
 	double f[L::Q], u[3], rho;
-	if (fluid)
-	{
-		pull_populations<L>(a, p, r, id, w, f);
-		update_site<L, COLL, FORCE, TAVG>(a, id, f, rho, u);
-	}
-	else load_own<L>(a, id, f);
+	pull_warp<L>(a, p, r, id, w, fluid, through, mode, f);
+	if (fluid) update_site<L, COLL, FORCE, TAVG>(a, id, f, rho, u);
 	store_populations<L>(a, id, f);
 	if (!fluid) return;
 	if (PEER) store_outgoing<L>(a, p, r, f);

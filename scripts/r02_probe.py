@@ -12,14 +12,17 @@ def defs(case, res):
                              L_REGULARISED_BOUNDARIES=True, L_NO_FLOW=True)
     if case == "box":        # closed box, all walls solid, no lid: no list kernel at all
         return E.Definitions(L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=1000.0, L_NO_FLOW=True)
-    if case.startswith("walls_"):      # walls_xyz: which axes carry solid walls (the others are periodic), e.g. walls_y = the channel
-        ax = case[6:]
+    if case.startswith("walls_"):      # walls_xyz: which axes carry solid walls (the others are periodic), e.g. walls_y = the channel;
+        ax = case[6:]                  # walls_z4 / walls_z32: z-walls 4 / 32 cells thick (whole sectors / whole warps solid)
+        zt = 1
+        if ax.startswith("z") and ax[1:].isdigit():
+            zt, ax = int(ax[1:]), "z"
         S, F = E.eSolid, E.eFluid
         w = lambda a: S if a in ax else F
         t = lambda a: 1 if a in ax else 0
         return E.Definitions(L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=None, L_NU=1.0 / res, L_NO_FLOW=True,
                              L_WALL_LEFT=w("x"), L_WALL_RIGHT=w("x"), L_WALL_BOTTOM=w("y"), L_WALL_TOP=w("y"), L_WALL_FRONT=w("z"), L_WALL_BACK=w("z"),
-                             L_WALL_THICKNESS_CELLS=(t("x"), t("x"), t("y"), t("y"), t("z"), t("z")))
+                             L_WALL_THICKNESS_CELLS=(t("x"), t("x"), t("y"), t("y"), t("z") * zt, t("z") * zt))
     force = case == "channel_f"
     smag = case == "channel_s"
     return E.Definitions(L_DIMS=3, L_RESOLUTION=res, L_TIMESTEP=0.05 / res, L_RE=None, L_NU=1.0 / res, L_NO_FLOW=True,
@@ -76,7 +79,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if mode == "walls2":        # the sector-completing stores (default) against LUMA_B200_FILL=0
         for res, st in ((256, 300), (384, 100)):
-            for case in ("walls_", "walls_z", "walls_xyz", "cavity", "channel_f", "channel_s"):
+            for case in ("walls_", "walls_z", "walls_z4", "walls_z32", "walls_xyz", "cavity", "channel_f", "channel_s"):
                 run(case, res, st)
                 run(case, res, st, {"LUMA_B200_FILL": "0"})
         sys.exit(0)
