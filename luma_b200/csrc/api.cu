@@ -142,7 +142,9 @@ struct luma_b200
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
 	int geometry_epoch = 0;         // bumped by upload / init_synthetic
-	bool fill_holes = true;         // solid sites at wall-bounded row ends join the stores of their sector (LUMA_B200_FILL=0 turns it off)
+	bool fill_holes = true;         // solid sites at wall-bounded row ends join the stores of their sector, link sites take the select
+	                                // sequence: decided per geometry (walls or bodies bounded in z); LUMA_B200_FILL=0 / 1 forces it off / on
+	int fill_env = -1;              // -1 automatic, 0 off, 1 on
 	int use_tma = 0;                // LUMA_B200_TMA=1 / LUMA_B200_V2=1 at create: measured variants of k_step (profiles/r02_variants.txt)
 	bool profiling = false;
 	std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop) recorded during the current step call
@@ -359,7 +361,8 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 		const char *tv = getenv("LUMA_B200_TMA"), *v2 = getenv("LUMA_B200_V2");
 		h->use_tma = (tv && *tv && atoi(tv) != 0) ? 1 : ((v2 && *v2 && atoi(v2) != 0) ? 2 : 0);
 		const char *fv = getenv("LUMA_B200_FILL");
-		h->fill_holes = !(fv && *fv && atoi(fv) == 0);
+		h->fill_env = (fv && *fv) ? (atoi(fv) != 0 ? 1 : 0) : -1;
+		h->fill_holes = h->fill_env != 0;
 	}
 
 	int ndev = 0;
@@ -882,9 +885,29 @@ static int finalize_geometry(luma_b200_t *h, DescFn desc_of)
 		launch_force_general(h->cw, forced_dev, (int)forced.size(), class_shift, h->s_main);
 		h->st.kernel_launches++;
 	}
+	// Walls or bodies bounded along the fastest index (a fluid site whose z-neighbour -- y in 2-D -- is eSolid): k_step then completes the row-end sectors and
+	// resolves bounce-back without splitting the warp (step_site / pull_warp).  Grids without them (periodic or open in z)
+	// keep the plain sequence, which is ~1 % faster there (profiles/r02_probe_walls_after.txt).
+	int *zflag = reinterpret_cast<int *>(h->momex_dev);      // scratch
+	CK(cudaMemsetAsync(zflag, 0, sizeof(int), h->s_main));
+	{
+		// the two axis directions along the fastest-running index (z in 3-D, y in 2-D: K = 1)
+		uint32_t zmask = 0;
+		const int fast = (D == 3) ? 2 : 1;
+		for (int v = 0; v < Q - 1; ++v)
+		{
+			int nz = 0;
+			for (int d = 0; d < 3; ++d) nz += lat_c(Q, v, d) != 0;
+			if (nz == 1 && lat_c(Q, v, fast) != 0) zmask |= 1u << v;
+		}
+		if (zmask) launch_any_bits(h->cw, (long long)pb * h->MK, (long long)(pe - pb) * h->MK, zmask, zflag, h->s_main);
+	}
+	int zwalls = 0;
+	CK(cudaMemcpyAsync(&zwalls, zflag, sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
 	const cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(h->s_main);
 	cudaFree(forced_dev);
 	CK(e1); CK(e2);
+	h->fill_holes = h->fill_env < 0 ? zwalls != 0 : h->fill_env != 0;
 	return LUMA_B200_OK;
 }
 }  // extern "C++"

@@ -129,6 +129,8 @@ void launch_halo_wait(const unsigned long long *flags, unsigned long long value,
 void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value, cudaStream_t s);
 void launch_force_general(uint32_t *cw, const long long *ids, int n, int class_shift, cudaStream_t s);
 void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
+// *flag |= 1 if any cell word in [first, first + n) has one of the bits in `mask`
+void launch_any_bits(const uint32_t *cw, long long first, long long n, uint32_t mask, int *flag, cudaStream_t s);
 template <class L> void launch_cell_words(const GeomArgs &g, cudaStream_t s);
 template <class L> void launch_synthetic(const SynthArgs &a, cudaStream_t s);
 // f = feq(rho, u) on sites [first, first + n): LBM_initGrid's population initialisation (init_grids.cpp:310-333)

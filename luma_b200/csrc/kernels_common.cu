@@ -18,6 +18,19 @@ void launch_force_general(uint32_t *cw, const long long *ids, int n, int class_s
 	if (n > 0) k_force_general<<<(n + 127) / 128, 128, 0, s>>>(cw, ids, n, class_shift);
 }
 
+// does any site carry one of the link bits in `mask`?  (geometry finalisation: are there walls / bodies bounded in z?)
+__global__ void k_any_bits(const uint32_t *__restrict__ cw, long long first, long long n, uint32_t mask, int *flag)
+{
+	bool hit = false;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+		hit = hit || (cw[first + i] & mask) != 0u;
+	if (__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+void launch_any_bits(const uint32_t *cw, long long first, long long n, uint32_t mask, int *flag, cudaStream_t s)
+{
+	if (n > 0) k_any_bits<<<148 * 8, 256, 0, s>>>(cw, first, n, mask, flag);
+}
+
 __global__ void k_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;

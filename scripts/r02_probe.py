@@ -83,6 +83,12 @@ if __name__ == "__main__":
                 run(case, res, st)
                 run(case, res, st, {"LUMA_B200_FILL": "0"})
         sys.exit(0)
+    if mode == "walls3":        # automatic choice per geometry vs forced on / off
+        for case in ("cavity", "channel_f", "walls_z", "walls_y"):
+            run(case, 256, 300)
+            run(case, 256, 300, {"LUMA_B200_FILL": "1"})
+            run(case, 256, 300, {"LUMA_B200_FILL": "0"})
+        sys.exit(0)
     if mode == "one":           # a single configuration (for ncu): one <case> <res> [ENV=VALUE ...]
         run(sys.argv[2], int(sys.argv[3]), 20, dict(kv.split("=", 1) for kv in sys.argv[4:]))
         sys.exit(0)

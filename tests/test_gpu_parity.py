@@ -396,3 +396,20 @@ def test_binary_restart_round_trip_continues_bitwise(name, tmp_path):
     with pytest.raises(capi.LumaB200Error):
         other.io_restart_read(path)
     other.close(); b.close(); ref.close()
+
+
+@pytest.mark.parametrize("fill", ["0", "1"])
+@pytest.mark.parametrize("name", ["cav3d_32", "chan3d", "cyl3d", "thin3d", "odd3d", "thickwall3d", "cav2d_64", "kbc3d_chan", "cav3d_tav"])
+def test_sector_completing_stores_and_select_path_are_bitwise_either_way(name, fill, monkeypatch):
+    """k_step's handling of walls along the fastest index -- solid row-end sites joining their sector's stores, bounce-back resolved by a
+    warp-uniform select sequence instead of a divergent branch (step_site / pull_warp) -- is chosen per geometry; forced on and forced
+    off (LUMA_B200_FILL) both must reproduce the oracle bit for bit, whatever the geometry"""
+    monkeypatch.setenv("LUMA_B200_FILL", fill)
+    case = CASES[name]
+    ref = port.PortGrid(case)
+    g = luma_b200.GridObj(defs_from_case(case)).LBM_initGrid()
+    monkeypatch.delenv("LUMA_B200_FILL")
+    for s in (1, 20):
+        g.LBM_multi_opt(s - g.t); ref.step(s - ref.t)
+        _assert_same(name, "fill=%s t%d" % (fill, s), g.download(), ref, g)
+    g.close(); ref.close()
