@@ -215,7 +215,11 @@ int  luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c);
  *      launch-bound grids collect LUMA_B200_GRAPH_STEPS steps into one CUDA-graph launch even when the host calls
  *      once per step (src/main_lbm.cpp:441).  Every entry point that reads state -- download*, forces, stats, sync --
  *      submits what is held back first; luma_b200_flush submits without reading or waiting (call it before a long
- *      stretch of host work).  A halo time-out (dead ring neighbour) is reported by the next call that notices it. ---- */
+ *      stretch of host work).  A halo time-out (dead ring neighbour) is reported by the next call that notices it.
+ *      Several ranks: a rank's step t+1 needs its ring neighbours' step t, so a rank must not block on another rank (MPI_Barrier,
+ *      MPI_Recv ...) while it still holds an accepted step back that the other rank's pending read needs.  Hosts that take
+ *      their read points collectively (LUMA's loop does: every rank steps and writes output at the same t) never can; any
+ *      other host calls luma_b200_flush before it blocks on a peer. ---- */
 int  luma_b200_step(luma_b200_t *h, int32_t nsteps);
 int  luma_b200_flush(luma_b200_t *h);
 

@@ -190,12 +190,14 @@ static void make_constants(LbmConst &C, int Q)
 	for (int k = 0; k < 4; ++k) C.wden[k] = C.w[k] / C.den;
 }
 
+// next (start or stop) event of the per-kernel profile, or nullptr when the runtime cannot create one: the caller then
+// skips the pair and the launch is simply not part of the profile
 static cudaEvent_t prof_event(luma_b200_t *h)
 {
 	if (h->prof_used == h->prof_ev.size())
 	{
 		cudaEvent_t e = nullptr;
-		cudaEventCreate(&e);
+		if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
 		h->prof_ev.push_back(e);
 	}
 	return h->prof_ev[h->prof_used++];
@@ -208,11 +210,19 @@ static cudaEvent_t prof_event(luma_b200_t *h)
 template <class L>
 static void main_kernel(luma_b200_t *h, const StepArgs &a, int coll, int force, int nplanes)
 {
-	if (h->profiling && nplanes > 0) cudaEventRecord(prof_event(h), h->s_main);
-	launch_step<L>(a, coll, force, nplanes, h->s_main, &h->st.kernel_launches);
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	if (h->profiling && nplanes > 0)
 	{
-		cudaEventRecord(prof_event(h), h->s_main);
+		const size_t used = h->prof_used;
+		e0 = prof_event(h);
+		e1 = e0 ? prof_event(h) : nullptr;
+		if (!e1) { h->prof_used = used; e0 = nullptr; }      // events come in (start, stop) pairs or not at all
+	}
+	if (e0) cudaEventRecord(e0, h->s_main);
+	launch_step<L>(a, coll, force, nplanes, h->s_main, &h->st.kernel_launches);
+	if (e1)
+	{
+		cudaEventRecord(e1, h->s_main);
 		h->st.step_kernel_launches++;
 		h->st.step_kernel_cells += (long long)nplanes * h->MK;
 	}

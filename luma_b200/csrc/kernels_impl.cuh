@@ -28,6 +28,9 @@ namespace luma {
 #ifndef LUMA_MIN_BLOCKS_KBC
 #define LUMA_MIN_BLOCKS_KBC 3   /* KBC keeps the own-site populations, ds and dh alive beside feq */
 #endif
+#ifndef LUMA_SMAG_RECOMPUTE
+#define LUMA_SMAG_RECOMPUTE 0   /* 1: k_step's Smagorinsky variant evaluates the equilibrium twice instead of keeping it in registers */
+#endif
 #ifndef LUMA_LOAD_MODE
 #define LUMA_LOAD_MODE 0      /* 0 ld.global.nc (__ldg), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate, 3 plain */
 #endif
@@ -162,6 +165,20 @@ __device__ __forceinline__ void pull_warp(const StepArgs &a, const int p, const 
 
 // BGK(/Smagorinsky) collision with optional Guo forcing, GridObj::_LBM_collide_opt (optimised.cpp:765-790),
 // or the KBC operator _LBM_kbcCollide_opt (:1122-1305), which replaces f by the collided own-site populations
+// f += omega_s * (feq - f) (+ Guo force), the relaxation of GridObj::_LBM_collide_opt (optimised.cpp:775-787)
+template <class L, int FORCE>
+__device__ __forceinline__ void relax(const StepArgs &a, const double (&u)[3], const double (&feq)[L::Q], const double omega_s, double (&f)[L::Q])
+{
+#pragma unroll
+	for (int v = 0; v < L::Q; ++v)
+	{
+		if constexpr (FORCE != 0)
+			f[v] = f[v] + (omega_s * (feq[v] - f[v]) + guo_force<L, (FORCE > 0 ? FORCE - 1 : 0)>(v, u, a.Fg, a.C, a.lam));
+		else
+			f[v] = f[v] + omega_s * (feq[v] - f[v]);
+	}
+}
+
 template <class L, int COLL, int FORCE>
 __device__ __forceinline__ void collide(const StepArgs &a, const long long id, const double (&u)[3], const double (&feq)[L::Q], double (&f)[L::Q])
 {
@@ -174,14 +191,7 @@ __device__ __forceinline__ void collide(const StepArgs &a, const long long id, c
 	}
 	double omega_s = a.omega;
 	if (COLL == COLL_SMAG) omega_s = smagorinsky_omega<L>(f, feq, a.tau, a.smag_coef);
-#pragma unroll
-	for (int v = 0; v < L::Q; ++v)
-	{
-		if constexpr (FORCE != 0)
-			f[v] = f[v] + (omega_s * (feq[v] - f[v]) + guo_force<L, (FORCE > 0 ? FORCE - 1 : 0)>(v, u, a.Fg, a.C, a.lam));
-		else
-			f[v] = f[v] + omega_s * (feq[v] - f[v]);
-	}
+	relax<L, FORCE>(a, u, feq, omega_s, f);
 }
 
 template <class L>
@@ -333,9 +343,29 @@ __device__ __forceinline__ void tavg_update(const StepArgs &a, const long long i
 template <class L, int COLL, int FORCE, bool TAVG>
 __device__ __forceinline__ void update_site(const StepArgs &a, const long long id, double (&f)[L::Q], double &rho, double (&u)[3])
 {
-	double feq[L::Q];
 	macroscopic<L, FORCE>(f, a.hFg, rho, u);
 	if (TAVG) tavg_update<L>(a, id, rho, u, 1);
+#if LUMA_SMAG_RECOMPUTE
+	if constexpr (COLL == COLL_SMAG)
+	{
+		// Smagorinsky needs the equilibrium twice -- for the non-equilibrium stress that gives omega_s, then for the relaxation --
+		// and keeping it would hold f AND feq (76 registers) live across the sqrt / division chain.  It is evaluated twice instead
+		// (the same expression on the same operands: identical bits); the empty asm keeps the compiler from merging the two.
+		double omega_s;
+		{
+			double feq1[L::Q];
+			equilibrium_all<L>(rho, u, a.C, feq1);
+			omega_s = smagorinsky_omega<L>(f, feq1, a.tau, a.smag_coef);
+		}
+		double r2 = rho, u2[3] = { u[0], u[1], u[2] };
+		asm volatile("" : "+d"(r2), "+d"(u2[0]), "+d"(u2[1]), "+d"(u2[2]), "+d"(omega_s));
+		double feq2[L::Q];
+		equilibrium_all<L>(r2, u2, a.C, feq2);
+		relax<L, FORCE>(a, u2, feq2, omega_s, f);
+		return;
+	}
+#endif
+	double feq[L::Q];
 	equilibrium_all<L>(rho, u, a.C, feq);
 	collide<L, COLL, FORCE>(a, id, u, feq, f);
 }

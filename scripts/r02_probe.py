@@ -89,6 +89,35 @@ if __name__ == "__main__":
             run(case, 256, 300, {"LUMA_B200_FILL": "1"})
             run(case, 256, 300, {"LUMA_B200_FILL": "0"})
         sys.exit(0)
+    if mode == "smag":          # the Smagorinsky kernel: periodic channel and the configs[3] geometry at reduced length
+        print("== library:", os.environ.get("LUMA_B200_LIB", "default"), flush=True)
+        run("channel_s", 256, 300)
+        run("channel_s", 384, 100)
+        run("cavity", 256, 300)
+        d = E.Definitions(L_DIMS=3, L_RESOLUTION=256, L_TIMESTEP=0.05 / 256, L_BX=2.0, L_BY=1.0, L_BZ=1.0, L_RE=7600.0, L_NO_FLOW=True,
+                          L_USE_BGKSMAG=True, L_CSMAG=0.3, L_VELOCITY_RAMP=0.5, L_WALL_LEFT=E.eVelocity, L_WALL_RIGHT=E.ePressure,
+                          L_WALL_FRONT=E.eFluid, L_WALL_BACK=E.eFluid, L_WALL_THICKNESS_CELLS=(1, 1, 1, 1, 0, 0), body_box=(128, 160, 112, 144, 0, 256))
+        g = E.GridObj(d).LBM_initGrid()
+        g.LBM_multi_opt(10); g.sync()
+        best = None
+        for _ in range(2):
+            g.LBM_multi_opt(150); st = g.stats()
+            best = st["ms_per_step"] if best is None else min(best, st["ms_per_step"])
+        cells = 512 * 256 * 256
+        print("c4-like 512x256x256 inlet/outlet + cylinder + Smagorinsky: step %.4f ms  %6.0f MLUPS  %5.0f GB/s" % (best, cells / best / 1e3, cells * 304 / best / 1e6), flush=True)
+        g.close()
+        sys.exit(0)
+    if mode == "c1":            # BASELINE configs[0]: 256^2 D2Q9 cavity Re=100, batched call
+        d = E.Definitions(L_DIMS=2, L_RESOLUTION=256, L_TIMESTEP=0.05 / 256, L_RE=100.0, L_UX0=1.0, L_WALL_TOP=E.eVelocity,
+                          L_REGULARISED_BOUNDARIES=True, L_NO_FLOW=True)
+        g = E.GridObj(d).LBM_initGrid()
+        g.LBM_multi_opt(200); g.sync()
+        for n in (8000, 8000):
+            g.LBM_multi_opt(n); st = g.stats()
+            print("C1 256^2 D2Q9 cavity, Python batch call of %d steps: %.3f us/step  %.0f MLUPS  graph launches so far %d" % (
+                n, 1e3 * st["ms_per_step"], st["mlups_last_call"], st["graph_launches"]), flush=True)
+        g.close()
+        sys.exit(0)
     if mode == "one":           # a single configuration (for ncu): one <case> <res> [ENV=VALUE ...]
         run(sys.argv[2], int(sys.argv[3]), 20, dict(kv.split("=", 1) for kv in sys.argv[4:]))
         sys.exit(0)
