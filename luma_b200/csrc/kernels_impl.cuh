@@ -23,13 +23,15 @@ namespace luma {
 #define LUMA_MIN_BLOCKS 6
 #endif
 #ifndef LUMA_MIN_BLOCKS_SMAG
-#define LUMA_MIN_BLOCKS_SMAG 5  /* measured on B200: 5 x 128 threads (<= 102 registers, no spills) beats 4 and 3; 6 spills */
+#define LUMA_MIN_BLOCKS_SMAG 6  /* with LUMA_SMAG_RECOMPUTE the Smagorinsky kernel fits 80 registers: 6 x 128 threads like BGK
+                                   (measured: +7 % over 5 CTAs x 96 registers with the equilibrium kept, profiles/r02_probe_smag.txt) */
 #endif
 #ifndef LUMA_MIN_BLOCKS_KBC
 #define LUMA_MIN_BLOCKS_KBC 3   /* KBC keeps the own-site populations, ds and dh alive beside feq */
 #endif
 #ifndef LUMA_SMAG_RECOMPUTE
-#define LUMA_SMAG_RECOMPUTE 0   /* 1: k_step's Smagorinsky variant evaluates the equilibrium twice instead of keeping it in registers */
+#define LUMA_SMAG_RECOMPUTE 1   /* k_step's Smagorinsky variant evaluates the equilibrium twice instead of keeping it in registers
+                                   (0 + LUMA_MIN_BLOCKS_SMAG=5: the round-1 form) */
 #endif
 #ifndef LUMA_LOAD_MODE
 #define LUMA_LOAD_MODE 0      /* 0 ld.global.nc (__ldg), 1 ld.global.cs, 2 ld.global.nc.L1::no_allocate, 3 plain */
@@ -358,7 +360,9 @@ __device__ __forceinline__ void update_site(const StepArgs &a, const long long i
 			omega_s = smagorinsky_omega<L>(f, feq1, a.tau, a.smag_coef);
 		}
 		double r2 = rho, u2[3] = { u[0], u[1], u[2] };
+#ifdef __CUDACC__
 		asm volatile("" : "+d"(r2), "+d"(u2[0]), "+d"(u2[1]), "+d"(u2[2]), "+d"(omega_s));
+#endif
 		double feq2[L::Q];
 		equilibrium_all<L>(r2, u2, a.C, feq2);
 		relax<L, FORCE>(a, u2, feq2, omega_s, f);
