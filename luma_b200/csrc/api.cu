@@ -132,15 +132,16 @@ struct luma_b200
 	LumaStats st;
 	std::string err;
 	// device-initiated halo exchange (NVLink peer stores); falls back to NCCL send/recv when not attached
-	unsigned long long *flags = nullptr;   // [0] exchange number that arrived from the left neighbour, [1] from the right; +4: counter
+	unsigned long long *flags = nullptr;   // [0] exchange number that arrived from the left neighbour, [1] from the right; [4]: block counter of
+	                                       // k_halo_push; [5]: this rank's own exchange number (advanced on the device: the launches are replayable)
 	int *halo_timeout = nullptr;           // set by k_halo_wait when a neighbour never showed up (device view of a mapped host word)
 	volatile int *halo_timeout_host = nullptr;   // the same word as the host reads it: polled without any stream traffic
 	PeerMap peer[2];                       // 0 = left (rank-1), 1 = right (rank+1); peer[1] aliases peer[0] when nranks == 2
 	bool p2p = false;
 	bool fused = false;                    // the face kernels store into the neighbours' ghost planes themselves (default with peer stores; LUMA_B200_FUSED_HALO=0: copy kernel)
-	unsigned long long xchg = 0;           // exchanges published so far
 	GraphSlot graphs[2];            // captured batches of graph_steps steps, one per lattice parity
 	int graph_steps = 0;            // 0 = never use graphs
+	bool graph_slabs = true;        // batches on slabs too (device-initiated exchange only); LUMA_B200_GRAPH_SLABS=0 turns them off
 	int geometry_epoch = 0;         // bumped by upload / init_synthetic
 	bool fill_holes = true;         // solid sites at wall-bounded row ends join the stores of their sector, link sites take the select
 	                                // sequence: decided per geometry (walls or bodies bounded in z); LUMA_B200_FILL=0 / 1 forces it off / on
@@ -365,6 +366,8 @@ int luma_b200_create(luma_b200_t **out, const LumaCaseParams *p)
 		int gsteps = (gsv && *gsv) ? atoi(gsv) : 16;
 		if (gsteps < 2 || h->cells > limit) gsteps = 0;
 		h->graph_steps = gsteps & ~1;
+		const char *sv = getenv("LUMA_B200_GRAPH_SLABS");
+		h->graph_slabs = !(sv && *sv && atoi(sv) == 0);
 	}
 	h->nu = (1.0 / h->omega - 0.5) * h->C.cs2;
 	{
@@ -522,6 +525,7 @@ int luma_b200_p2p_attach(luma_b200_t *h, const void *left_blob, const void *righ
 		pm.f[0] = (double *)pm.base[0]; pm.f[1] = (double *)pm.base[1]; pm.flags = (unsigned long long *)pm.base[2];
 	}
 	h->p2p = true;
+	for (GraphSlot &g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
 	{
 		// the peer stores are part of the face kernels' epilogue (default: measured best at every slab size,
 		// profiles/r02_halo_transports_n2.txt); LUMA_B200_FUSED_HALO=0 keeps the separate copy kernel k_halo_push
@@ -577,9 +581,8 @@ static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s, bool
 	if (already_stored)
 	{
 		// fused exchange: k_step_faces / k_bc of this step wrote the neighbours' ghost planes; only the arrival flags remain
-		const unsigned long long value = ++h->xchg;
-		launch_halo_publish(h->peer[0].flags + 1, h->peer[1].flags + 0, value, s);
-		launch_halo_wait(h->flags, value, h->halo_timeout, s);
+		launch_halo_publish(h->peer[0].flags + 1, h->peer[1].flags + 0, h->flags + 5, s);
+		launch_halo_wait(h->flags, h->flags + 5, h->halo_timeout, s);
 		h->st.kernel_launches += 2;
 		CK(cudaGetLastError());
 		return LUMA_B200_OK;
@@ -605,10 +608,10 @@ static int exchange_populations_p2p(luma_b200_t *h, int li, cudaStream_t s, bool
 	a.count = h->MK;
 	a.peer_flag[0] = h->peer[0].flags + 1;      // we are the left neighbour's RIGHT neighbour
 	a.peer_flag[1] = h->peer[1].flags + 0;      // and the right neighbour's LEFT neighbour
-	a.value = ++h->xchg;
+	a.seq = h->flags + 5;
 	a.done = reinterpret_cast<unsigned int *>(h->flags + 4);
 	launch_halo_push(a, s);
-	launch_halo_wait(h->flags, a.value, h->halo_timeout, s);
+	launch_halo_wait(h->flags, h->flags + 5, h->halo_timeout, s);
 	h->st.kernel_launches += 2;
 	CK(cudaGetLastError());
 	return LUMA_B200_OK;
@@ -1252,20 +1255,52 @@ static int enqueue_step_live(luma_b200_t *h, StepArgs &x, int coll, int force)
 	return LUMA_B200_OK;
 }
 
-// the same step as a self-contained fork/join on the capturing stream (single rank only): the body of the CUDA graphs
+// the same step as a self-contained fork/join on the capturing stream: the body of the CUDA graphs.  Slabs: only with the
+// device-initiated exchange (its launches take no per-step argument: the exchange number lives on the device).
 static int enqueue_step_captured(luma_b200_t *h, StepArgs &x, int coll, int force)
 {
-	x.p0 = 0; x.pstep = 1;
-	const bool side = h->n_bc > 0;
-	if (side)
+	if (!h->ghost)
 	{
-		CK(cudaEventRecord(h->ev_fork, h->s_main));
-		CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
-		LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
-		CK(cudaEventRecord(h->ev_join, h->s_comm));
+		x.p0 = 0; x.pstep = 1;
+		const bool side = h->n_bc > 0;
+		if (side)
+		{
+			CK(cudaEventRecord(h->ev_fork, h->s_main));
+			CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
+			LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
+			CK(cudaEventRecord(h->ev_join, h->s_comm));
+		}
+		LAT(h->Q, launch_step<L>(x, coll, force, h->P, h->s_main, &h->st.kernel_launches));
+		if (side) CK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+		return LUMA_B200_OK;
 	}
-	LAT(h->Q, launch_step<L>(x, coll, force, h->P, h->s_main, &h->st.kernel_launches));
-	if (side) CK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
+	const int owned = h->p.x_count;
+	const bool fused = h->fused;
+	if (fused)
+	{
+		const int lo = (x.fout == h->f[0]) ? 0 : 1;
+		for (int sd = 0; sd < 2; ++sd)
+		{
+			x.peer_f[sd] = h->peer[sd].f[lo];
+			x.peer_stride[sd] = h->peer[sd].stride;
+			x.peer_P[sd] = h->peer[sd].P;
+		}
+	}
+	StepArgs e = x;
+	e.p0 = 1; e.pstep = (owned > 1) ? owned - 1 : 1;
+	const int nedge = (owned > 1) ? 2 : 1;
+	StepArgs in = x;
+	in.p0 = 2; in.pstep = 1;
+	CK(cudaEventRecord(h->ev_fork, h->s_main));
+	CK(cudaStreamWaitEvent(h->s_comm, h->ev_fork, 0));
+	LAT(h->Q, launch_bc<L>(x, coll, force, h->s_comm, &h->st.kernel_launches));
+	if (fused) LAT(h->Q, launch_step_faces<L>(e, coll, force, nedge, h->s_comm, &h->st.kernel_launches));
+	else LAT(h->Q, launch_step<L>(e, coll, force, nedge, h->s_comm, &h->st.kernel_launches));
+	const int rc = exchange_populations(h, x.fout, h->s_comm, fused);
+	if (rc) return rc;
+	CK(cudaEventRecord(h->ev_join, h->s_comm));
+	LAT(h->Q, launch_step<L>(in, coll, force, owned - 2, h->s_main, &h->st.kernel_launches));
+	CK(cudaStreamWaitEvent(h->s_main, h->ev_join, 0));
 	return LUMA_B200_OK;
 }
 
@@ -1316,7 +1351,8 @@ static int drain(luma_b200_t *h, bool final)
 	// into a CUDA graph -- same kernels, same arguments, the two streams become graph branches -- and replayed with
 	// one launch each.  Only while every per-step scalar is constant (ramps finished, no time averages, no profiling
 	// events), on a single rank, and never for a step that stores rho,u.
-	const bool graph_capable = GS >= 2 && !h->ghost && !h->profiling && !h->tav;
+	// Slabs qualify with the device-initiated exchange (LUMA_B200_GRAPH_SLABS=0 keeps them on live launches).
+	const bool graph_capable = GS >= 2 && (!h->ghost || (h->p2p && h->graph_slabs)) && !h->profiling && !h->tav;
 	auto graph_ready = [&](int t_now) -> bool
 	{
 		if (!graph_capable) return false;

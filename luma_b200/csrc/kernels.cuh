@@ -81,7 +81,7 @@ struct HaloPushArgs
 	int nmsg;
 	long long count;          // M*K
 	unsigned long long *peer_flag[2];   // the neighbours' arrival flags for data coming from this rank
-	unsigned long long value; // exchange number being published
+	unsigned long long *seq;  // this rank's exchange number (device memory; advanced by the publishing kernel)
 	unsigned int *done;       // local block counter (zero between launches)
 };
 
@@ -125,8 +125,8 @@ template <class L> void launch_bc(const StepArgs &a, int coll, int force, cudaSt
 template <class L> void launch_step_faces(const StepArgs &a, int coll, int force, int nplanes, cudaStream_t s, int64_t *launches);
 template <class L> void launch_velsrc(const VelSrcArgs &a, cudaStream_t s, int64_t *launches);
 void launch_halo_push(const HaloPushArgs &a, cudaStream_t s);
-void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s);
-void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value, cudaStream_t s);
+void launch_halo_wait(const unsigned long long *flags, const unsigned long long *seq, int *timed_out, cudaStream_t s);
+void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long *seq, cudaStream_t s);
 void launch_force_general(uint32_t *cw, const long long *ids, int n, int class_shift, cudaStream_t s);
 void launch_scatter_u32(uint32_t *out, const long long *ids, const uint32_t *vals, int n, cudaStream_t s);
 // *flag |= 1 if any cell word in [first, first + n) has one of the bits in `mask`

@@ -64,9 +64,11 @@ __global__ void __launch_bounds__(256) k_halo_push(const HaloPushArgs a)
 		if (atomicAdd(a.done, 1u) == total - 1)
 		{
 			*a.done = 0;
+			const unsigned long long value = *a.seq + 1;      // this rank's exchange number lives on the device (see k_halo_publish)
+			*a.seq = value;
 			__threadfence_system();
 			for (int side = 0; side < 2; ++side)
-				asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a.peer_flag[side]), "l"(a.value) : "memory");
+				asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a.peer_flag[side]), "l"(value) : "memory");
 		}
 	}
 }
@@ -74,16 +76,20 @@ __global__ void __launch_bounds__(256) k_halo_push(const HaloPushArgs a)
 // the flag part alone, for the fused exchange: the face kernels (k_step_faces, k_bc) of this step have already stored
 // the populations into the neighbours' ghost planes and have completed (stream order); the release below is cumulative
 // over those stores
-__global__ void k_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value)
+// The exchange number is a counter in this rank's own device memory, advanced here, not a value the host passes in: the
+// launch arguments are then the same for every step and a batch of steps can be captured into a CUDA graph and replayed.
+__global__ void k_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long *seq)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const unsigned long long value = *seq + 1;
+	*seq = value;
 	__threadfence_system();
 	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(left_flag), "l"(value) : "memory");
 	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(right_flag), "l"(value) : "memory");
 }
-void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long value, cudaStream_t s)
+void launch_halo_publish(unsigned long long *left_flag, unsigned long long *right_flag, unsigned long long *seq, cudaStream_t s)
 {
-	k_halo_publish<<<1, 32, 0, s>>>(left_flag, right_flag, value);
+	k_halo_publish<<<1, 32, 0, s>>>(left_flag, right_flag, seq);
 }
 
 void launch_halo_push(const HaloPushArgs &a, cudaStream_t s)
@@ -98,10 +104,12 @@ void launch_halo_push(const HaloPushArgs &a, cudaStream_t s)
 // 20 s (a dead peer must not hang the GPU) and reports it through *timed_out, a word in mapped host memory that
 // the host polls.  Once it is set every later wait returns at once: the queued steps drain in microseconds
 // (on stale ghost planes -- the call that notices the flag returns LUMA_B200_ENCCL and the state is void).
-__global__ void k_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out)
+__global__ void k_halo_wait(const unsigned long long *flags, const unsigned long long *seq, int *timed_out)
 {
 	if (threadIdx.x > 1) return;
 	if (*reinterpret_cast<volatile int *>(timed_out) != 0) return;
+	// the exchange this rank has just published (same stream, earlier kernel): its neighbours' data of the same number must be in
+	const unsigned long long value = *reinterpret_cast<const volatile unsigned long long *>(seq);
 	unsigned long long t0, t1, seen;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 	for (;;)
@@ -114,9 +122,9 @@ __global__ void k_halo_wait(const unsigned long long *flags, unsigned long long 
 	}
 }
 
-void launch_halo_wait(const unsigned long long *flags, unsigned long long value, int *timed_out, cudaStream_t s)
+void launch_halo_wait(const unsigned long long *flags, const unsigned long long *seq, int *timed_out, cudaStream_t s)
 {
-	k_halo_wait<<<1, 32, 0, s>>>(flags, value, timed_out);
+	k_halo_wait<<<1, 32, 0, s>>>(flags, seq, timed_out);
 }
 
 void launch_u_aos_to_soa(const double *aos, double *soa, long long stride, int ncomp, long long first, long long n, cudaStream_t s)
