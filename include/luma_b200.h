@@ -213,7 +213,7 @@ int  luma_b200_init_synthetic(luma_b200_t *h, const LumaSyntheticCase *c);
  *      is held back until the next call or read point, because the last step before the host looks at the fields is
  *      the one that stores rho,u (all others keep them in registers; the host may look at main_lbm.cpp:449-561), and
  *      launch-bound grids collect LUMA_B200_GRAPH_STEPS steps into one CUDA-graph launch even when the host calls
- *      once per step (src/main_lbm.cpp:441).  Every entry point that reads state -- download*, forces, stats, sync --
+ *      once per step (src/main_lbm.cpp:441) -- single rank, and slabs with the device-initiated exchange.  Every entry point that reads state -- download*, forces, stats, sync --
  *      submits what is held back first; luma_b200_flush submits without reading or waiting (call it before a long
  *      stretch of host work).  A halo time-out (dead ring neighbour) is reported by the next call that notices it.
  *      Several ranks: a rank's step t+1 needs its ring neighbours' step t, so a rank must not block on another rank (MPI_Barrier,
