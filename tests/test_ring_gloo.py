@@ -120,41 +120,48 @@ class _FakeGrid:
         self.attached = True
 
 
-def _attach_worker(rank, world, port_no, scenario, q):
+SCENARIOS = (("all_ok", True), ("export_fails_on_1", False), ("attach_fails_everywhere", False), ("attach_fails_on_1", "raised"))
+
+
+def _attach_worker(rank, world, port_no, q):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port_no)
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        export_ok = not (scenario == "export_fails_on_1" and rank == 1)
-        attach_ok = not (scenario == "attach_fails_on_1" and rank == 1) and scenario != "attach_fails_everywhere"
-        g = _FakeGrid(export_ok, attach_ok)
-        try:
-            res = ring.attach_p2p(dist, g, rank, world)
-        except RuntimeError as ex:
-            res = "raised"
-        dist.barrier()
+        out = []
+        for scenario, _ in SCENARIOS:
+            export_ok = not (scenario == "export_fails_on_1" and rank == 1)
+            attach_ok = not (scenario == "attach_fails_on_1" and rank == 1) and scenario != "attach_fails_everywhere"
+            g = _FakeGrid(export_ok, attach_ok)
+            try:
+                res = ring.attach_p2p(dist, g, rank, world)
+            except RuntimeError:
+                res = "raised"
+            dist.barrier()
+            out.append((scenario, res, g.attached))
         dist.destroy_process_group()
-        q.put((rank, res, g.attached))
+        q.put((rank, out))
     except Exception:   # pragma: no cover
         import traceback
-        q.put((rank, "FAIL: " + traceback.format_exc(), False))
+        q.put((rank, "FAIL: " + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("scenario,expect", [("all_ok", True), ("export_fails_on_1", False), ("attach_fails_everywhere", False),
-                                             ("attach_fails_on_1", "raised")])
-def test_transport_choice_is_collective(scenario, expect):
+def test_transport_choice_is_collective():
     """ring.attach_p2p: every rank ends with the same answer -- peer stores everywhere, NCCL everywhere (and then NO rank has
-    attached), or an exception everywhere when the mappings opened on some ranks only"""
+    attached when the export failed), or an exception everywhere when the mappings opened on some ranks only"""
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = _free_port()
-    procs = [ctx.Process(target=_attach_worker, args=(r, world, port_no, scenario, q)) for r in range(world)]
+    procs = [ctx.Process(target=_attach_worker, args=(r, world, port_no, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=240) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    assert [r[1] for r in res] == [expect] * world, res
-    if expect is False:
-        assert not any(r[2] for r in res) or scenario == "attach_fails_everywhere", res
+    assert all(isinstance(r[1], list) for r in res), res
+    for i, (scenario, expect) in enumerate(SCENARIOS):
+        got = [r[1][i] for r in res]
+        assert [g[1] for g in got] == [expect] * world, (scenario, got)
+        if scenario == "export_fails_on_1":
+            assert not any(g[2] for g in got), got
