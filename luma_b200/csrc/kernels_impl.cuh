@@ -29,6 +29,11 @@ namespace luma {
 #ifndef LUMA_MIN_BLOCKS_KBC
 #define LUMA_MIN_BLOCKS_KBC 3   /* KBC keeps the own-site populations, ds and dh alive beside feq */
 #endif
+#ifndef LUMA_VARIANTS
+#define LUMA_VARIANTS 0         /* 1: also build the two measured-and-retired forms of k_step (k_step_v2: two sites per thread with 128-bit
+                                   accesses, LUMA_B200_V2=1; k_step_tma: loads staged through shared memory by the TMA engine,
+                                   LUMA_B200_TMA=1) -- luma_b200.build.build_variant("variants", ["-DLUMA_VARIANTS=1"]); profiles/r02_variants.txt */
+#endif
 #ifndef LUMA_SMAG_RECOMPUTE
 #define LUMA_SMAG_RECOMPUTE 1   /* k_step's Smagorinsky variant evaluates the equilibrium twice instead of keeping it in registers
                                    (0 + LUMA_MIN_BLOCKS_SMAG=5: the round-1 form) */
@@ -374,22 +379,6 @@ __device__ __forceinline__ void update_site(const StepArgs &a, const long long i
 	collide<L, COLL, FORCE>(a, id, u, feq, f);
 }
 
-template <class L, int COLL, int FORCE, bool TAVG, bool PEER>
-__device__ __forceinline__ void step_one(const StepArgs &a, const int p, const unsigned r, const long long id, const uint32_t w)
-{
-	double f[L::Q], u[3], rho;
-	pull_populations<L>(a, p, r, id, w, f);
-	update_site<L, COLL, FORCE, TAVG>(a, id, f, rho, u);
-	store_populations<L>(a, id, f);
-	if (PEER) store_outgoing<L>(a, p, r, f);
-	if (a.write_macro)
-	{
-		a.rho[id] = rho;
-#pragma unroll
-		for (int d = 0; d < L::D; ++d) a.u[(long long)d * a.stride + id] = u[d];
-	}
-}
-
 // Pass-through of never-updated sites (eSolid, eRefined, non-regularised eVelocity) that share a 32-byte sector with a site
 // this kernel updates -- the solid site at each end of a wall-bounded z-row: k = 0 solid, k = 1, 2, 3 fluid.  Without it the
 // warp's store covers 24 of the sector's 32 bytes, and the L2 has to fetch the sector from DRAM to rebuild its ECC (ncu:
@@ -440,6 +429,7 @@ __device__ __forceinline__ void step_site(const StepArgs &a)
 	}
 }
 
+#if LUMA_VARIANTS
 // ------------------------------------------------------------------------------------------------
 // Variant of k_step with TWO z-adjacent sites per thread and 128-bit accesses (LUMA_B200_V2=1; measured against the
 // one-site kernel in profiles/r02_variants.txt).  Sites (r, r+1), r even: all Q stores and the loads of the populations
@@ -497,6 +487,8 @@ __global__ void __launch_bounds__(STEP_THREADS, LUMA_MIN_BLOCKS_V2) k_step_v2(co
 #endif
 }
 
+#endif  // LUMA_VARIANTS
+
 template <class L, int COLL, int FORCE, bool TAVG>
 __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_step(const StepArgs a)
 {
@@ -511,6 +503,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step_faces(const StepArgs a)
 	step_site<L, COLL, FORCE, TAVG, true>(a);
 }
 
+#if LUMA_VARIANTS
 // ------------------------------------------------------------------------------------------------
 // Variant of k_step whose loads are STAGED THROUGH SHARED MEMORY BY THE TMA ENGINE (LUMA_B200_TMA=1; measured against
 // the per-thread-load kernel in profiles/r02_variants.txt).  One CTA = one run of STEP_THREADS consecutive sites of an
@@ -609,6 +602,8 @@ __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<L, COLL>()) k_st
 	}
 #endif
 }
+
+#endif  // LUMA_VARIANTS
 
 // new-time rho,u of an extrapolation neighbour: GridObj::_LBM_updateAndExtrapolate +
 // _LBM_updateInteriorLatticeSite (optimised.cpp:1353-1434).  A fluid neighbour is streamed and
@@ -908,6 +903,7 @@ template <class L> void launch_step(const StepArgs &a, int coll, int force, int 
 	if (nplanes <= 0) return;
 	dim3 grid((a.MK + STEP_THREADS - 1) / STEP_THREADS, (unsigned)nplanes);
 	// the TMA-staged variant needs even M*K and K (16-byte aligned bulk copies) and the start of a tile on an even element
+#if LUMA_VARIANTS
 	if (a.use_tma == 1 && (a.MK & 1u) == 0 && (a.K & 1) == 0) LUMA_DISPATCH(k_step_tma, grid, STEP_THREADS);
 	else if (a.use_tma == 2 && (a.MK & 1u) == 0 && (a.K & 1) == 0 && L::D == 3)
 	{
@@ -922,7 +918,9 @@ template <class L> void launch_step(const StepArgs &a, int coll, int force, int 
 		}
 		if (launches) ++*launches;
 	}
-	else LUMA_DISPATCH(k_step, grid, STEP_THREADS);
+	else
+#endif
+	LUMA_DISPATCH(k_step, grid, STEP_THREADS);
 	if (launches) ++*launches;
 }
 
