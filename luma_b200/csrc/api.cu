@@ -1688,8 +1688,11 @@ static int restart_stream(luma_b200_t *h, FILE *fh, bool write, double *soa_or_f
 	// one field of `ncomp` doubles per site (ncomp = 1: plain copy; > 1: device SoA <-> file AoS), owned planes only
 	const long long owned = (long long)h->p.x_count * h->MK, dev_off = (long long)h->ghost * h->MK;
 	const long long chunk = std::max<long long>(h->MK, std::min<long long>(owned, (long long)(64u << 20) / (ncomp * 8)));
-	int rc = ensure_staging(h, (size_t)chunk * h->Q * sizeof(double));
-	if (rc) return rc;
+	if (soa)
+	{
+		const int rc = ensure_staging(h, (size_t)chunk * ncomp * sizeof(double));      // layout conversion goes through the staging buffer
+		if (rc) return rc;
+	}
 	std::vector<double> host((size_t)chunk * ncomp);
 	for (long long c0 = 0; c0 < owned; c0 += chunk)
 	{
